@@ -1,0 +1,231 @@
+/*
+ * pnslam.h -- C ABI of the B200-native differentiable ray-rendering path.
+ *
+ * The reference (thua919/pointNeRF-SLAM, a NICE-SLAM fork) is pure Python: it
+ * has no FFI for this path, only Python call signatures.  This
+ * header is therefore the boundary a maintainer binds with ctypes; each entry
+ * point names the reference lines whose ATen op chain it replaces.  All
+ * pointers are DEVICE pointers unless stated; `stream` is a cudaStream_t.
+ * Every function returns 0 on success, non-zero on error; pn_last_error()
+ * returns a thread-local message.  The library keeps no global mutable state
+ * and never caches caller pointers across calls.
+ *
+ * Layout conventions
+ *   - feature grids are channels-last: [Z][Y][X][32] float32 (the memory of a
+ *     torch (1,32,Z,Y,X) tensor in torch.channels_last_3d format);
+ *   - "planar-4" stash buffers hold an (N x K) float matrix as
+ *     [K/4][N] float4, i.e. element (n,k) at ((k/4)*N + n)*4 + k%4, so that
+ *     consecutive samples are consecutive 16-byte words;
+ *   - decoder parameters are read in place from the torch tensors of the
+ *     nn.Module (row-major [out][in]).
+ */
+#ifndef PNSLAM_H_
+#define PNSLAM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_HIDDEN 32 /* hidden width of the NICE decoders, decoder.py:295 */
+#define PN_EMBED 93  /* Fourier mapping size, decoder.py:129 */
+#define PN_CDIM 32   /* feature channels per grid, nice_slam.yaml:114 */
+#define PN_MAX_SAMPLES 128
+
+typedef struct pn_grid {
+  const float* data; /* [D][H][W][32] */
+  int D, H, W;       /* Z, Y, X voxel counts */
+} pn_grid;
+
+/* Parameters of one decoder.MLP (decoder.py:91-203) with hidden 32, 5 blocks,
+ * skip after block 2.  in-dims of W: 93,32,32,125,32.  c_dim 32 or 64. */
+typedef struct pn_grid_mlp {
+  const float* B;     /* embedder._B (3,93) */
+  const float* W[5];  /* pts_linears.i.weight */
+  const float* b[5];  /* pts_linears.i.bias */
+  const float* Wc[5]; /* fc_c.i.weight (32,c_dim) */
+  const float* bc[5]; /* fc_c.i.bias */
+  const float* Wo;    /* output_linear.weight (n_out,32) */
+  const float* bo;    /* output_linear.bias */
+  int c_dim;
+  int n_out; /* 1 (occupancy) or 4 (colour) */
+} pn_grid_mlp;
+
+/* Gradient sinks with the shapes of pn_grid_mlp (accumulated with +=; the
+ * caller zeroes them).  Any pointer may be NULL (that gradient is skipped). */
+typedef struct pn_grid_mlp_grad {
+  float* B;
+  float* W[5];
+  float* b[5];
+  float* Wc[5];
+  float* bc[5];
+  float* Wo;
+  float* bo;
+} pn_grid_mlp_grad;
+
+/* Parameters of decoder.MLP_no_xyz (decoder.py:206-274): in-dims 32,32,32,64,32. */
+typedef struct pn_coarse_mlp {
+  const float* W[5];
+  const float* b[5];
+  const float* Wo;
+  const float* bo;
+} pn_coarse_mlp;
+
+typedef struct pn_coarse_mlp_grad {
+  float* W[5];
+  float* b[5];
+  float* Wo;
+  float* bo;
+} pn_coarse_mlp_grad;
+
+/* Where the sample points of an evaluation come from.  Exactly one of
+ * pts64 / pts32 / (rays_o, rays_d, z) is set.  In ray mode sample n is
+ * (ray n / S, k = n % S) and p = o + d * z[ray][k] evaluated in float64
+ * (Renderer.py:177-179). */
+typedef struct pn_points {
+  const double* pts64; /* (N,3) */
+  const float* pts32;  /* (N,3) */
+  const float* rays_o; /* (R,3) */
+  const float* rays_d; /* (R,3) */
+  const double* z;     /* (R,S) */
+  int S;
+  int64_t N; /* number of sample points */
+} pn_points;
+
+/* Stash written by a forward evaluation for its backward. */
+typedef struct pn_stash {
+  uint32_t* relu_bits; /* [5][N]: bit j of word i = (pre-activation j of block i > 0) */
+  float* H;            /* [5] planar-4 (N x 32): block outputs h_0..h_4; NULL unless weight grads wanted */
+  float* C;            /* planar-4 (N x c_dim): gathered features; NULL unless weight grads wanted */
+  float* E;            /* planar-4 (N x 96): Fourier embedding (cols 93..95 zero); NULL unless weight grads wanted */
+} pn_stash;
+
+/* Scratch written by the input-gradient kernel for the weight-gradient kernel. */
+typedef struct pn_wscratch {
+  float* GA;   /* [5] planar-4 (N x 32): gradient at block pre-activations */
+  float* GH;   /* [5] planar-4 (N x 32): gradient at block outputs */
+  float* GARG; /* planar-4 (N x 96): gradient at the Fourier arguments */
+  float* P32;  /* [3][N]: float32 points */
+  float* GO;   /* (N,4): gradient at the decoder outputs actually consumed (masked) */
+} pn_wscratch;
+
+enum { PN_OUT_SET_ALL = 0, /* raw[n] = (0,0,0,occ) or the 4 colour-decoder outputs */
+       PN_OUT_SET_W = 1,   /* raw[n].w = occ, rgb kept */
+       PN_OUT_ADD_W = 2 }; /* raw[n].w += occ */
+
+const char* pn_last_error(void);
+int pn_version(void);
+
+/* -------- pose and ray generation (src/common.py:74-176, 248-266) -------- */
+
+/* get_camera_from_tensor, common.py:163-176: cam (B,7) [qw qx qy qz tx ty tz] -> c2w (B,3,4). */
+int pn_camera_from_tensor_fwd(const float* cam, int batch, float* c2w, void* stream);
+/* its vector-Jacobian product: g_c2w (B,3,4) -> g_cam (B,7) (overwritten). */
+int pn_camera_from_tensor_bwd(const float* cam, const float* g_c2w, int batch, float* g_cam, void* stream);
+
+/* get_samples without the randint, common.py:92-134: for flat crop indices idx (n,)
+ * gather depth/colour and build rays.  c2w: 12+ floats, row stride `c2w_ld` (4 for
+ * (3,4)/(4,4) row-major).  color_img float32 or float64 (H,W,3) selected by color_is_f64;
+ * color_out has the same dtype. */
+int pn_sample_rays_fwd(const int64_t* idx, int n, int H0, int W0, int Wc, int W,
+                       float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                       const float* depth_img, const void* color_img, int color_is_f64,
+                       float* rays_o, float* rays_d, float* depth_out, void* color_out, void* stream);
+/* get_rays, common.py:248-266: all H*W rays, row-major. */
+int pn_image_rays_fwd(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                      float* rays_o, float* rays_d, void* stream);
+/* VJP of both: g_c2w (3,4) += sum_n [ g_rays_d[n] (x) dir_n | g_rays_o[n] ].  Pixels given
+ * either by idx (+crop) or, if idx == NULL, as the full H0..,W0.. Wc-wide lattice of n pixels.
+ * Block reduction by warp shuffles, one atomicAdd per block and entry.  g_c2w must be zeroed. */
+int pn_rays_bwd(const int64_t* idx, int n, int H0, int W0, int Wc, float fx, float fy, float cx, float cy,
+                const float* g_rays_o, const float* g_rays_d, float* g_c2w, void* stream);
+
+/* -------- sample placement (src/utils/Renderer.py:82-175) -------- */
+
+/* Depth-guided + stratified z-values, sorted.  gt_depth may be NULL (then n_surface
+ * is ignored, near = 0.01, far = box exit).  depth_max: device pointer to max(gt_depth)
+ * over the WHOLE batch (all shards).  bound: host array [lo_x hi_x lo_y hi_y lo_z hi_z]
+ * float64.  t_vals: device linspace(0,1,n_samples) float32; t_surface: device
+ * linspace(0,1,n_surface) as float64 (both made by the host with torch.linspace so that
+ * they carry the reference's exact values).  t_rand: optional (R,n_samples) jitter for
+ * perturb>0.  z_out: (R, S). */
+int pn_ray_zvals(const float* rays_o, const float* rays_d, const float* gt_depth, const float* depth_max,
+                 int64_t R, const double* bound, int n_samples, int n_surface, int lindisp,
+                 const float* t_vals, const double* t_surface, const float* t_rand, double* z_out,
+                 void* stream);
+/* sample_pdf (common.py:19-63) + merge-sort (Renderer.py:187-191): z (R,S), weights (R,S)
+ * -> z_out (R,S+n_imp).  u_lin: device linspace(0,1,n_imp) (deterministic mode) or
+ * u_rand: (R,n_imp) uniforms; exactly one is used (u_rand wins). */
+int pn_importance_zvals(const double* z, const float* weights, int64_t R, int S, int n_imp,
+                        const float* u_lin, const float* u_rand, double* z_out, void* stream);
+/* sample_pdf alone (common.py:19-63): bins (R,nb) f64, weights (R,nb-1) f32 -> out (R,n) f64. */
+int pn_sample_pdf(const double* bins, const float* weights, int64_t R, int nb, int n, const float* u_lin,
+                  const float* u_rand, double* out, void* stream);
+/* regulation sample points (Renderer.py:280-298), all float32: z jittered in [0, 0.85*depth]
+ * with t_rand (R,n_samples), pts_out (R*n_samples,3) = o + d*z; z_out (optional) gets z as
+ * float64 (R,n_samples) for pn_points_to_rays_bwd. */
+int pn_regulation_points(const float* rays_o, const float* rays_d, const float* gt_depth, const float* t_vals,
+                         const float* t_rand, int64_t R, int n_samples, float* pts_out, double* z_out,
+                         void* stream);
+
+/* -------- decoders (src/conv_onet/models/decoder.py) -------- */
+
+/* One decoder.MLP over N points: trilinear gather (decoder.py:168-175), Fourier
+ * embedding (26-30), 5 blocks + output (189-203).  gridA is the decoder's own grid,
+ * gridB the middle grid concatenated (detached) when w->c_dim == 64 (182-187).
+ * norm_bound / mask_bound: host float64[6].  If apply_mask, points outside
+ * mask_bound (strict) get raw.w = 100 (Renderer.py:43-57).  raw: (N,4) float32. */
+int pn_grid_mlp_fwd(const pn_points* pts, const pn_grid_mlp* w, const pn_grid* gridA, const pn_grid* gridB,
+                    const double* norm_bound, const double* mask_bound, int apply_mask, int out_mode,
+                    float* raw, const pn_stash* stash, void* stream);
+/* Input-side backward of the same decoder.  g_raw (N,4): this decoder consumes
+ * components 0..2 (n_out 4) or component 3 (n_out 1; zeroed outside mask_bound if
+ * apply_mask).  Produces (each optional): g_gridA [D][H][W][32] += (warp-aggregated
+ * vector atomics), g_pts (N,3) float32 (=/+= per accumulate_pts), and the scratch the
+ * weight-gradient kernel needs. */
+int pn_grid_mlp_bwd(const pn_points* pts, const pn_grid_mlp* w, const pn_grid* gridA, const pn_grid* gridB,
+                    const double* norm_bound, const double* mask_bound, int apply_mask,
+                    const float* g_raw, const pn_stash* stash, float* g_gridA, float* g_pts,
+                    int accumulate_pts, const pn_wscratch* ws, void* stream);
+/* Weight gradients: sum over samples of (gradient x activation) outer products, as
+ * tiled FFMA GEMMs over the stash/scratch; results atomically added into `g`. */
+int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash* stash, const pn_wscratch* ws,
+                      const pn_grid_mlp_grad* g, void* stream);
+
+/* decoder.MLP_no_xyz (coarse level).  Same conventions; norm_bound is the enlarged bound. */
+int pn_coarse_mlp_fwd(const pn_points* pts, const pn_coarse_mlp* w, const pn_grid* grid,
+                      const double* norm_bound, const double* mask_bound, int apply_mask, int out_mode,
+                      float* raw, const pn_stash* stash, void* stream);
+int pn_coarse_mlp_bwd(const pn_points* pts, const pn_coarse_mlp* w, const pn_grid* grid,
+                      const double* norm_bound, const double* mask_bound, int apply_mask,
+                      const float* g_raw, const pn_stash* stash, float* g_grid, float* g_pts,
+                      int accumulate_pts, const pn_wscratch* ws, void* stream);
+int pn_coarse_mlp_wgrad(int64_t N, const pn_stash* stash, const pn_wscratch* ws,
+                        const pn_coarse_mlp_grad* g, void* stream);
+
+/* -------- compositing (src/common.py:204-245) -------- */
+
+/* raw (R,S,4), z (R,S) f64, rays_d (R,3) -> depth (R) f64, var (R) f64, rgb (R,3) f32,
+ * weights (R,S) f32 (optional).  One warp per ray, transmittance by warp scan. */
+int pn_composite_fwd(const float* raw, const double* z, const float* rays_d, int64_t R, int S, int occupancy,
+                     double* depth, double* var, float* rgb, float* weights, void* stream);
+/* VJP: g_depth, g_var (f64, optional), g_rgb (f32, optional) -> g_raw (R,S,4).  In density
+ * mode alpha depends on |rays_d|; that term is added (+=) into g_rays_d (R,3) if non-NULL. */
+int pn_composite_bwd(const float* raw, const double* z, const float* rays_d, int64_t R, int S, int occupancy,
+                     const double* g_depth, const double* g_var, const float* g_rgb, float* g_raw,
+                     float* g_rays_d, void* stream);
+/* VJP of p = o + d*z: g_pts (R*S,3) -> g_rays_o (R,3), g_rays_d (R,3), float64 accumulation. */
+int pn_points_to_rays_bwd(const float* g_pts, const double* z, int64_t R, int S,
+                          float* g_rays_o, float* g_rays_d, void* stream);
+
+/* -------- utilities -------- */
+/* (1,32,Z,Y,X) contiguous <-> channels-last [Z][Y][X][32]; `to_channels_last` = 1 or 0. */
+int pn_grid_transpose(const float* src, float* dst, int D, int H, int W, int to_channels_last, void* stream);
+/* out[0] = max(x[0..n)) ; n >= 1. */
+int pn_max_f32(const float* x, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNSLAM_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of ``libpnslam.so`` (the C ABI declared in ``include/pnslam.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call
+fails, a ``RuntimeError`` is raised (the reference's error convention is Python
+exceptions only).  PyTorch is used by the callers of this module
+only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpnslam.so")
+BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
+
+P = C.c_void_p
+
+
+class PnGrid(C.Structure):
+    _fields_ = [("data", P), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
+class PnGridMlp(C.Structure):
+    _fields_ = [("B", P), ("W", P * 5), ("b", P * 5), ("Wc", P * 5), ("bc", P * 5), ("Wo", P), ("bo", P),
+                ("c_dim", C.c_int), ("n_out", C.c_int)]
+
+
+class PnGridMlpGrad(C.Structure):
+    _fields_ = [("B", P), ("W", P * 5), ("b", P * 5), ("Wc", P * 5), ("bc", P * 5), ("Wo", P), ("bo", P)]
+
+
+class PnCoarseMlp(C.Structure):
+    _fields_ = [("W", P * 5), ("b", P * 5), ("Wo", P), ("bo", P)]
+
+
+class PnCoarseMlpGrad(C.Structure):
+    _fields_ = [("W", P * 5), ("b", P * 5), ("Wo", P), ("bo", P)]
+
+
+class PnImapMlp(C.Structure):
+    _fields_ = [("B", P), ("W", P * 8), ("b", P * 8), ("Wo", P), ("bo", P), ("hidden", C.c_int), ("n_blocks", C.c_int)]
+
+
+class PnPoints(C.Structure):
+    _fields_ = [("pts64", P), ("pts32", P), ("rays_o", P), ("rays_d", P), ("z", P), ("S", C.c_int), ("N", C.c_int64)]
+
+
+class PnStash(C.Structure):
+    _fields_ = [("relu_bits", P), ("H", P), ("C", P), ("E", P)]
+
+
+class PnWscratch(C.Structure):
+    _fields_ = [("GA", P), ("GH", P), ("GARG", P), ("P32", P), ("GO", P)]
+
+
+OUT_SET_ALL, OUT_SET_W, OUT_ADD_W = 0, 1, 2
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library once per process; raise loudly if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                f"Build it with `bash {BUILD_SCRIPT}` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pn_last_error.restype = C.c_char_p
+        _lib.pn_version.restype = C.c_int
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{what} failed: {lib().pn_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f64x6(bound) -> C.Array:
+    """(3,2) bound -> host double[6] = [lo_x hi_x lo_y hi_y lo_z hi_z]."""
+    if isinstance(bound, torch.Tensor):
+        vals = bound.detach().to("cpu", torch.float64).reshape(-1).tolist()
+    else:
+        vals = [float(v) for row in bound for v in row]
+    return (C.c_double * 6)(*vals)
+
+
+def fill_ptr_array(arr, tensors: Sequence[Optional[torch.Tensor]]) -> None:
+    for i, t in enumerate(tensors):
+        arr[i] = ptr(t)

@@ -1,0 +1,36 @@
+// Error reporting and device queries shared by all C-ABI entry points.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "pn_common.cuh"
+
+namespace pn {
+namespace {
+thread_local char g_err[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_status(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+  return 1;
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      n <= 0)
+    return 148;  // B200
+  return n;
+}
+}  // namespace pn
+
+extern "C" const char* pn_last_error(void) { return pn::g_err; }
+extern "C" int pn_version(void) { return 100; }

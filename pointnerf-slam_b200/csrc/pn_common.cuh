@@ -1,0 +1,161 @@
+// Shared device helpers for the sm_100a ray-rendering kernels.
+//
+// Geometry (sample points, bound test, coordinate normalisation) follows the
+// reference's mixed float32/float64 arithmetic op by op with explicitly
+// rounded intrinsics (no FMA contraction), so that the in-bound mask and the
+// voxel a sample falls into are bit-identical to the reference's torch path:
+//   points      src/utils/Renderer.py:177-179   (float64: o + d*z)
+//   bound mask  src/utils/Renderer.py:43-46     (strict, in the points' dtype)
+//   normalise   src/common.py:269-284           (in the points' dtype, then .float())
+//   trilinear   F.grid_sample(align_corners=True, padding_mode='border'),
+//               src/conv_onet/models/decoder.py:168-175
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pnslam.h"
+
+namespace pn {
+
+constexpr int kThreads = 256;          // threads per CTA of the per-sample kernels
+constexpr int kLdc = kThreads + 1;     // padded row of the per-CTA feature tile
+constexpr unsigned kFull = 0xffffffffu;
+
+void set_error(const char* fmt, ...);
+int launch_status(const char* what);   // cudaGetLastError -> 0 / 1 (+message)
+int sm_count();
+
+struct Bound6 {  // [lo_x hi_x lo_y hi_y lo_z hi_z]
+  double v[6];
+};
+inline Bound6 make_bound(const double* b) {
+  Bound6 r;
+  for (int i = 0; i < 6; ++i) r.v[i] = b ? b[i] : 0.0;
+  return r;
+}
+
+struct GridDev {
+  const float* data;
+  int D, H, W;
+};
+inline GridDev make_grid(const pn_grid* g) {
+  GridDev r{nullptr, 1, 1, 1};
+  if (g) { r.data = g->data; r.D = g->D; r.H = g->H; r.W = g->W; }
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// sample point, bound mask, normalised coordinate
+// ---------------------------------------------------------------------------
+struct Sample {
+  float pf[3];   // float32 point fed to the Fourier embedding (p.float())
+  float xn[3];   // normalised coordinate in [-1,1] (float32, after .float())
+  bool inside;   // strictly inside mask bound
+};
+
+__device__ __forceinline__ void load_sample(const pn_points& ps, int64_t n, const Bound6& nb, const Bound6& mb,
+                                            Sample& s) {
+  if (ps.pts32) {  // float32 points: everything in float32 with the bound cast to float32
+    bool in = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float p = ps.pts32[3 * n + a];
+      s.pf[a] = p;
+      in = in && (p < (float)mb.v[2 * a + 1]) && (p > (float)mb.v[2 * a]);
+      const float ext = (float)__dsub_rn(nb.v[2 * a + 1], nb.v[2 * a]);
+      const float t = __fdiv_rn(__fsub_rn(p, (float)nb.v[2 * a]), ext);
+      s.xn[a] = __fsub_rn(__fmul_rn(t, 2.0f), 1.0f);
+    }
+    s.inside = in;
+    return;
+  }
+  double p[3];
+  if (ps.pts64) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = ps.pts64[3 * n + a];
+  } else {
+    const int64_t r = n / ps.S;
+    const double z = ps.z[n];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      p[a] = __dadd_rn((double)ps.rays_o[3 * r + a], __dmul_rn((double)ps.rays_d[3 * r + a], z));
+  }
+  bool in = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    s.pf[a] = (float)p[a];
+    in = in && (p[a] < mb.v[2 * a + 1]) && (p[a] > mb.v[2 * a]);
+    const double t = __ddiv_rn(__dsub_rn(p[a], nb.v[2 * a]), __dsub_rn(nb.v[2 * a + 1], nb.v[2 * a]));
+    s.xn[a] = (float)__dsub_rn(__dmul_rn(t, 2.0), 1.0);
+  }
+  s.inside = in;
+}
+
+// d(xn)/d(p) factor of the normalisation, applied to a float32 gradient.
+__device__ __forceinline__ float norm_grad(const pn_points& ps, const Bound6& nb, int a, float g) {
+  if (ps.pts32) return __fdiv_rn(__fmul_rn(g, 2.0f), (float)__dsub_rn(nb.v[2 * a + 1], nb.v[2 * a]));
+  return (float)__ddiv_rn(__dmul_rn((double)g, 2.0), __dsub_rn(nb.v[2 * a + 1], nb.v[2 * a]));
+}
+
+// grid_sampler_unnormalize(align_corners=True): ((x+1)/2)*(size-1), float32.
+__device__ __forceinline__ float unnormalise(float xn, int size) {
+  return __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f), (float)(size - 1));
+}
+
+// One trilinear cell in ATen's corner order (tnw,tne,tsw,tse,bnw,bne,bsw,bse):
+// corner c has x-offset c&1, y-offset (c>>1)&1, z-offset c>>2.
+struct Cell {
+  int64_t base;        // ((z0*H + y0)*W + x0) * 32
+  float wx[2], wy[2], wz[2];  // [0] = weight of the low corner ((x0+1)-ix), [1] = ix-x0
+  unsigned ok;         // bit c set if corner c is inside the grid
+  float gm[3];         // (size-1)/2 if the coordinate was not clipped else 0
+};
+
+__device__ __forceinline__ Cell make_cell(float ux, float uy, float uz, int W, int H, int D) {
+  Cell c;
+  const float mx = (float)(W - 1), my = (float)(H - 1), mz = (float)(D - 1);
+  const float ix = fminf(mx, fmaxf(ux, 0.0f));
+  const float iy = fminf(my, fmaxf(uy, 0.0f));
+  const float iz = fminf(mz, fmaxf(uz, 0.0f));
+  c.gm[0] = (ux <= 0.0f || ux >= mx) ? 0.0f : 0.5f * mx;
+  c.gm[1] = (uy <= 0.0f || uy >= my) ? 0.0f : 0.5f * my;
+  c.gm[2] = (uz <= 0.0f || uz >= mz) ? 0.0f : 0.5f * mz;
+  const float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
+  const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+  c.wx[1] = __fsub_rn(ix, fx0); c.wx[0] = __fsub_rn(fx0 + 1.0f, ix);
+  c.wy[1] = __fsub_rn(iy, fy0); c.wy[0] = __fsub_rn(fy0 + 1.0f, iy);
+  c.wz[1] = __fsub_rn(iz, fz0); c.wz[0] = __fsub_rn(fz0 + 1.0f, iz);
+  const bool x1 = (x0 + 1) < W, y1 = (y0 + 1) < H, z1 = (z0 + 1) < D;
+  unsigned ok = 1u;
+  ok |= x1 ? 2u : 0u;
+  ok |= y1 ? 4u : 0u;
+  ok |= (x1 && y1) ? 8u : 0u;
+  if (z1) ok |= ok << 4;
+  c.ok = ok;
+  c.base = (((int64_t)z0 * H + y0) * W + x0) * 32;
+  return c;
+}
+
+__device__ __forceinline__ float corner_weight(const Cell& c, int k) {
+  return __fmul_rn(__fmul_rn(c.wx[k & 1], c.wy[(k >> 1) & 1]), c.wz[k >> 2]);
+}
+
+__device__ __forceinline__ int64_t corner_offset(int k, int W, int H) {
+  return ((int64_t)(k & 1) + (int64_t)((k >> 1) & 1) * W + (int64_t)(k >> 2) * W * H) * 32;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// vector reduction into global memory: red.global.add.v4.f32 (sm_90+)
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace pn

@@ -1,0 +1,417 @@
+"""Host-side orchestration of the CUDA kernels: decoder passes, stashes and the
+two autograd boundaries (points -> raw, rays -> depth/variance/colour).
+
+Nothing here computes on the CPU; every numerical step is a call into
+``libpnslam.so``.  torch supplies device memory, streams and the autograd graph
+edges only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+GRID_KEYS = ("grid_coarse", "grid_middle", "grid_fine", "grid_color")
+
+
+# --------------------------------------------------------------------------
+# decoder parameter access (duck-typed: works for this package's modules and
+# for the reference's decoder.MLP / MLP_no_xyz / NICE instances alike)
+# --------------------------------------------------------------------------
+def grid_mlp_tensors(dec) -> List[torch.Tensor]:
+    """[B, W0..4, b0..4, Wc0..4, bc0..4, Wo, bo] (decoder.py:124-159 names)."""
+    ts = [dec.embedder._B]
+    ts += [l.weight for l in dec.pts_linears]
+    ts += [l.bias for l in dec.pts_linears]
+    ts += [l.weight for l in dec.fc_c]
+    ts += [l.bias for l in dec.fc_c]
+    ts += [dec.output_linear.weight, dec.output_linear.bias]
+    return ts
+
+
+def coarse_mlp_tensors(dec) -> List[torch.Tensor]:
+    """[W0..4, b0..4, Wo, bo] (decoder.py:235-245 names)."""
+    return ([l.weight for l in dec.pts_linears] + [l.bias for l in dec.pts_linears]
+            + [dec.output_linear.weight, dec.output_linear.bias])
+
+
+def imap_mlp_tensors(dec) -> List[torch.Tensor]:
+    """[B, W0.., b0.., Wo, bo] of the iMAP* single MLP (c_dim == 0)."""
+    return ([dec.embedder._B] + [l.weight for l in dec.pts_linears] + [l.bias for l in dec.pts_linears]
+            + [dec.output_linear.weight, dec.output_linear.bias])
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (this framework has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t
+
+
+def host_bound(bound) -> C.Array:
+    return L.f64x6(bound)
+
+
+# --------------------------------------------------------------------------
+# passes
+# --------------------------------------------------------------------------
+@dataclass
+class Pass:
+    kind: str                 # 'grid' | 'coarse' | 'imap'
+    dec: object               # decoder sub-module
+    grid_a: Optional[str]     # own grid key
+    grid_b: Optional[str]     # detached middle grid (fine decoder)
+    out_mode: int
+    norm_bound: object        # (3,2) bound used for coordinate normalisation
+    params: List[torch.Tensor] = field(default_factory=list)
+
+    def __post_init__(self):
+        if self.kind == "grid":
+            self.params = grid_mlp_tensors(self.dec)
+        elif self.kind == "coarse":
+            self.params = coarse_mlp_tensors(self.dec)
+        else:
+            self.params = imap_mlp_tensors(self.dec)
+
+    @property
+    def c_dim(self) -> int:
+        return self.dec.fc_c[0].weight.shape[1] if self.kind == "grid" else 0
+
+    @property
+    def n_out(self) -> int:
+        return self.dec.output_linear.weight.shape[0]
+
+
+def _dec_bound(dec, default):
+    b = getattr(dec, "bound", None)
+    return default if b is None else b
+
+
+def stage_passes(decoders, stage: str, default_bound) -> List[Pass]:
+    """Kernel passes that realise NICE.forward for a stage (decoder.py:312-342).
+    The colour decoder runs first so that the occupancy passes can overwrite /
+    accumulate the 4th component exactly as ``raw[..., -1] = fine + middle``."""
+    if stage == "coarse":
+        d = decoders.coarse_decoder
+        return [Pass("coarse", d, "grid_coarse", None, L.OUT_SET_ALL, _dec_bound(d, default_bound))]
+    mid = decoders.middle_decoder
+    p_mid = lambda mode: Pass("grid", mid, "grid_middle", None, mode, _dec_bound(mid, default_bound))
+    if stage == "middle":
+        return [p_mid(L.OUT_SET_ALL)]
+    fine = decoders.fine_decoder
+    p_fine = lambda mode: Pass("grid", fine, "grid_fine", "grid_middle", mode, _dec_bound(fine, default_bound))
+    if stage == "fine":
+        return [p_fine(L.OUT_SET_ALL), p_mid(L.OUT_ADD_W)]
+    if stage == "color":
+        col = decoders.color_decoder
+        return [Pass("grid", col, "grid_color", None, L.OUT_SET_ALL, _dec_bound(col, default_bound)),
+                p_fine(L.OUT_SET_W), p_mid(L.OUT_ADD_W)]
+    raise ValueError(f"unknown stage {stage!r}")
+
+
+def single_pass(dec, kind: str, default_bound) -> List[Pass]:
+    """One sub-decoder called on its own (MLP.forward / MLP_no_xyz.forward)."""
+    if kind == "imap":
+        return [Pass("imap", dec, None, None, L.OUT_SET_ALL, default_bound)]
+    name = dec.name
+    grid_b = "grid_middle" if (kind == "grid" and getattr(dec, "concat_feature", False)) else None
+    return [Pass(kind, dec, "grid_" + name, grid_b, L.OUT_SET_ALL, _dec_bound(dec, default_bound))]
+
+
+@dataclass
+class Plan:
+    passes: List[Pass]
+    mask_bound: Optional[object]      # None -> no out-of-bound override (decoder called directly)
+    grid_keys: List[str] = field(default_factory=list)
+
+    def __post_init__(self):
+        keys = []
+        for p in self.passes:
+            for k in (p.grid_a, p.grid_b):
+                if k is not None and k not in keys:
+                    keys.append(k)
+        self.grid_keys = keys
+
+    def flat_params(self) -> List[torch.Tensor]:
+        out: List[torch.Tensor] = []
+        for p in self.passes:
+            out += p.params
+        return out
+
+
+# --------------------------------------------------------------------------
+# grids
+# --------------------------------------------------------------------------
+def grid_channels_last(g: torch.Tensor) -> torch.Tensor:
+    """(1,32,Z,Y,X) tensor whose memory is [Z][Y][X][32].  A grid that already is
+    in torch.channels_last_3d format is used in place; a contiguous NCDHW grid
+    (the reference's layout) is transposed by the library."""
+    if g.dim() != 5 or g.shape[0] != 1 or g.shape[1] != 32:
+        raise RuntimeError(f"feature grid must be (1,32,Z,Y,X), got {tuple(g.shape)}")
+    if not g.is_cuda:
+        raise RuntimeError("feature grids must live on a CUDA device (this framework has no CPU path)")
+    if g.dtype != torch.float32:
+        raise RuntimeError("feature grids must be float32")
+    if g.is_contiguous(memory_format=torch.channels_last_3d):
+        return g
+    src = g.detach().contiguous()
+    out = torch.empty_like(src, memory_format=torch.channels_last_3d)
+    with torch.cuda.device(g.device):
+        L.check(L.lib().pn_grid_transpose(C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr()), g.shape[2], g.shape[3],
+                                          g.shape[4], 1, C.c_void_p(L.stream_ptr(g.device))), "pn_grid_transpose")
+    return out
+
+
+def new_grid_grad(g: torch.Tensor) -> torch.Tensor:
+    """Zeroed gradient buffer shaped like g with channels-last memory."""
+    return torch.zeros((1, g.shape[2], g.shape[3], g.shape[4], 32), device=g.device,
+                       dtype=torch.float32).permute(0, 4, 1, 2, 3)
+
+
+def _pn_grid(g: Optional[torch.Tensor]) -> Optional[L.PnGrid]:
+    if g is None:
+        return None
+    return L.PnGrid(g.data_ptr(), g.shape[2], g.shape[3], g.shape[4])
+
+
+# --------------------------------------------------------------------------
+# point sources
+# --------------------------------------------------------------------------
+@dataclass
+class Points:
+    n: int
+    pts: Optional[torch.Tensor] = None        # (N,3) float32 / float64
+    rays_o: Optional[torch.Tensor] = None     # (R,3) float32
+    rays_d: Optional[torch.Tensor] = None
+    z: Optional[torch.Tensor] = None          # (R,S) float64
+
+    def struct(self) -> L.PnPoints:
+        s = L.PnPoints()
+        s.N = self.n
+        if self.pts is not None:
+            if self.pts.dtype == torch.float64:
+                s.pts64 = self.pts.data_ptr()
+            else:
+                s.pts32 = self.pts.data_ptr()
+            s.S = 1
+        else:
+            s.rays_o, s.rays_d, s.z = self.rays_o.data_ptr(), self.rays_d.data_ptr(), self.z.data_ptr()
+            s.S = self.z.shape[1]
+        return s
+
+
+# --------------------------------------------------------------------------
+# forward / backward over a plan
+# --------------------------------------------------------------------------
+def _mlp_struct(p: Pass) -> L.PnGridMlp:
+    t = p.params
+    m = L.PnGridMlp()
+    m.B = t[0].data_ptr()
+    for i in range(5):
+        m.W[i] = t[1 + i].data_ptr(); m.b[i] = t[6 + i].data_ptr()
+        m.Wc[i] = t[11 + i].data_ptr(); m.bc[i] = t[16 + i].data_ptr()
+    m.Wo, m.bo = t[21].data_ptr(), t[22].data_ptr()
+    m.c_dim, m.n_out = p.c_dim, p.n_out
+    return m
+
+
+def _coarse_struct(p: Pass) -> L.PnCoarseMlp:
+    t = p.params
+    m = L.PnCoarseMlp()
+    for i in range(5):
+        m.W[i] = t[i].data_ptr(); m.b[i] = t[5 + i].data_ptr()
+    m.Wo, m.bo = t[10].data_ptr(), t[11].data_ptr()
+    return m
+
+
+def _byref(x):
+    return C.byref(x) if x is not None else None
+
+
+class Stash:
+    """Device buffers a forward pass leaves for its backward."""
+
+    def __init__(self, p: Pass, n: int, device, weights: bool):
+        self.relu_bits = torch.empty(5 * n, dtype=torch.int32, device=device)
+        self.H = self.C = self.E = None
+        if weights:
+            self.H = torch.empty(5 * 32 * n, dtype=torch.float32, device=device)
+            self.C = torch.empty(max(p.c_dim, 32) * n, dtype=torch.float32, device=device)
+            if p.kind == "grid":
+                self.E = torch.empty(96 * n, dtype=torch.float32, device=device)
+
+    def struct(self) -> L.PnStash:
+        return L.PnStash(self.relu_bits.data_ptr(), L.ptr(self.H), L.ptr(self.C), L.ptr(self.E))
+
+
+def plan_forward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, device, save: bool,
+                 want_w: Sequence[bool]) -> Tuple[torch.Tensor, List[Optional[Stash]]]:
+    """Run every pass of the plan; returns raw (N,4) and the per-pass stashes."""
+    lib = L.lib()
+    n = pts.n
+    raw = torch.empty((n, 4), dtype=torch.float32, device=device)
+    stashes: List[Optional[Stash]] = []
+    if n == 0:
+        return raw, [None] * len(plan.passes)
+    ps = pts.struct()
+    st = C.c_void_p(L.stream_ptr(device))
+    mb = host_bound(plan.mask_bound) if plan.mask_bound is not None else None
+    apply_mask = 1 if mb is not None else 0
+    with torch.cuda.device(device):
+        for i, p in enumerate(plan.passes):
+            stash = Stash(p, n, device, bool(want_w[i])) if save else None
+            stashes.append(stash)
+            sst = stash.struct() if stash is not None else None
+            nb = host_bound(p.norm_bound)
+            if p.kind == "grid":
+                m = _mlp_struct(p)
+                ga, gb = _pn_grid(grids_cl[p.grid_a]), _pn_grid(grids_cl.get(p.grid_b) if p.grid_b else None)
+                L.check(lib.pn_grid_mlp_fwd(C.byref(ps), C.byref(m), C.byref(ga), _byref(gb), nb, mb, apply_mask,
+                                            p.out_mode, C.c_void_p(raw.data_ptr()), _byref(sst), st), "pn_grid_mlp_fwd")
+            elif p.kind == "coarse":
+                m = _coarse_struct(p)
+                ga = _pn_grid(grids_cl[p.grid_a])
+                L.check(lib.pn_coarse_mlp_fwd(C.byref(ps), C.byref(m), C.byref(ga), nb, mb, apply_mask, p.out_mode,
+                                              C.c_void_p(raw.data_ptr()), _byref(sst), st), "pn_coarse_mlp_fwd")
+            else:
+                from . import imap
+                stashes[-1] = imap.forward(p, pts, raw, plan.mask_bound, device, save, bool(want_w[i]))
+    return raw, stashes
+
+
+def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, device, g_raw: torch.Tensor,
+                  stashes: List[Optional[Stash]], need_grid: Dict[str, bool], need_pts: bool,
+                  want_w: Sequence[bool]):
+    """Backward of plan_forward.  Returns (grid grads by key, g_pts or None,
+    per-pass parameter-gradient lists or None)."""
+    lib = L.lib()
+    n = pts.n
+    g_grids: Dict[str, torch.Tensor] = {k: new_grid_grad(grids_cl[k]) for k in plan.grid_keys if need_grid.get(k)}
+    g_pts = torch.zeros((n, 3), dtype=torch.float32, device=device) if need_pts else None
+    g_params: List[Optional[List[torch.Tensor]]] = []
+    if n == 0:
+        for i, p in enumerate(plan.passes):
+            g_params.append([torch.zeros_like(t) for t in p.params] if want_w[i] else None)
+        return g_grids, g_pts, g_params
+    ps = pts.struct()
+    st = C.c_void_p(L.stream_ptr(device))
+    mb = host_bound(plan.mask_bound) if plan.mask_bound is not None else None
+    apply_mask = 1 if mb is not None else 0
+    with torch.cuda.device(device):
+        for i, p in enumerate(plan.passes):
+            nb = host_bound(p.norm_bound)
+            gg = g_grids.get(p.grid_a) if p.grid_a else None
+            if p.kind == "imap":
+                from . import imap
+                g_params.append(imap.backward(p, pts, g_raw, stashes[i], g_pts, plan.mask_bound, device, bool(want_w[i])))
+                continue
+            ws = wst = None
+            if want_w[i]:
+                f32 = dict(dtype=torch.float32, device=device)
+                ws = dict(GA=torch.empty(5 * 32 * n, **f32), GH=torch.empty(5 * 32 * n, **f32),
+                          GARG=torch.empty(96 * n, **f32), P32=torch.empty(3 * n, **f32), GO=torch.empty(4 * n, **f32))
+                wst = L.PnWscratch(*[ws[k].data_ptr() for k in ("GA", "GH", "GARG", "P32", "GO")])
+            sst = stashes[i].struct()
+            if p.kind == "grid":
+                m = _mlp_struct(p)
+                ga, gb = _pn_grid(grids_cl[p.grid_a]), _pn_grid(grids_cl.get(p.grid_b) if p.grid_b else None)
+                L.check(lib.pn_grid_mlp_bwd(C.byref(ps), C.byref(m), C.byref(ga), _byref(gb), nb, mb, apply_mask,
+                                            C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
+                                            C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_grid_mlp_bwd")
+                if want_w[i]:
+                    gp = [torch.zeros_like(t) for t in p.params]
+                    g = L.PnGridMlpGrad()
+                    g.B = gp[0].data_ptr()
+                    for k in range(5):
+                        g.W[k] = gp[1 + k].data_ptr(); g.b[k] = gp[6 + k].data_ptr()
+                        g.Wc[k] = gp[11 + k].data_ptr(); g.bc[k] = gp[16 + k].data_ptr()
+                    g.Wo, g.bo = gp[21].data_ptr(), gp[22].data_ptr()
+                    L.check(lib.pn_grid_mlp_wgrad(C.c_int64(n), C.byref(m), C.byref(sst), C.byref(wst), C.byref(g), st),
+                            "pn_grid_mlp_wgrad")
+                    g_params.append(gp)
+                else:
+                    g_params.append(None)
+            else:  # coarse
+                m = _coarse_struct(p)
+                ga = _pn_grid(grids_cl[p.grid_a])
+                L.check(lib.pn_coarse_mlp_bwd(C.byref(ps), C.byref(m), C.byref(ga), nb, mb, apply_mask,
+                                              C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
+                                              C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_coarse_mlp_bwd")
+                if want_w[i]:
+                    gp = [torch.zeros_like(t) for t in p.params]
+                    g = L.PnCoarseMlpGrad()
+                    for k in range(5):
+                        g.W[k] = gp[k].data_ptr(); g.b[k] = gp[5 + k].data_ptr()
+                    g.Wo, g.bo = gp[10].data_ptr(), gp[11].data_ptr()
+                    L.check(lib.pn_coarse_mlp_wgrad(C.c_int64(n), C.byref(sst), C.byref(wst), C.byref(g), st),
+                            "pn_coarse_mlp_wgrad")
+                    g_params.append(gp)
+                else:
+                    g_params.append(None)
+    return g_grids, g_pts, g_params
+
+
+def _grad_flags(plan: Plan, needs: Sequence[bool], n_lead: int, freeze_map: bool):
+    """Split autograd's needs_input_grad (after the first n_lead inputs) into
+    per-grid and per-pass flags."""
+    ng = len(plan.grid_keys)
+    need_grid = {k: (bool(needs[n_lead + i]) and not freeze_map) for i, k in enumerate(plan.grid_keys)}
+    want_w = []
+    off = n_lead + ng
+    for p in plan.passes:
+        cnt = len(p.params)
+        want_w.append((not freeze_map) and any(needs[off:off + cnt]))
+        off += cnt
+    return need_grid, want_w
+
+
+def _assemble_grads(plan: Plan, needs: Sequence[bool], n_lead: int, g_grids, g_params):
+    out: List[Optional[torch.Tensor]] = []
+    for i, k in enumerate(plan.grid_keys):
+        out.append(g_grids.get(k) if needs[n_lead + i] else None)
+    off = n_lead + len(plan.grid_keys)
+    for p, gp in zip(plan.passes, g_params):
+        for j in range(len(p.params)):
+            out.append(gp[j] if (gp is not None and needs[off + j]) else None)
+        off += len(p.params)
+    return out
+
+
+class EvalPointsFn(torch.autograd.Function):
+    """points (N,3) -> raw (N,4) through the plan's decoders."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, freeze_map: bool, p: torch.Tensor, *tensors):
+        device = p.device
+        grids = {k: grid_channels_last(tensors[i]) for i, k in enumerate(plan.grid_keys)}
+        needs = ctx.needs_input_grad
+        need_grid, want_w = _grad_flags(plan, needs, 3, freeze_map)
+        save = any(needs)
+        pts = Points(n=p.shape[0], pts=p.detach().contiguous())
+        raw, stashes = plan_forward(plan, grids, pts, device, save, want_w)
+        if save:
+            ctx.plan, ctx.grids, ctx.pts, ctx.stashes = plan, grids, pts, stashes
+            ctx.need_grid, ctx.want_w, ctx.p_dtype = need_grid, want_w, p.dtype
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        needs = ctx.needs_input_grad
+        plan = ctx.plan
+        g_raw = g_raw.contiguous().float()
+        g_grids, g_pts, g_params = plan_backward(plan, ctx.grids, ctx.pts, g_raw.device, g_raw, ctx.stashes,
+                                                 ctx.need_grid, bool(needs[2]), ctx.want_w)
+        gp = g_pts.to(ctx.p_dtype) if g_pts is not None else None
+        return (None, None, gp, *_assemble_grads(plan, needs, 3, g_grids, g_params))
+
+
+def eval_plan(plan: Plan, p: torch.Tensor, c: Optional[dict], freeze_map: bool = False) -> torch.Tensor:
+    grids = [c[k] for k in plan.grid_keys]
+    return EvalPointsFn.apply(plan, freeze_map, p, *grids, *plan.flat_params())

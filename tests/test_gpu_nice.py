@@ -1,0 +1,248 @@
+"""GPU parity of the NICE path: CUDA kernels (through the C ABI) vs the CPU
+oracle on identical inputs, and vs the reference's golden vectors.
+
+Tolerances (stated per check):
+  * integer / index work and float64 geometry: bit-exact (pixel indices, rays,
+    z-values, out-of-bound mask);
+  * decoder outputs and rendered depth / colour: |err| <= 3e-4 + 1e-3*|ref|.
+    The floor is the float32 Fourier argument p@B (|arg| up to a few hundred
+    rad, 1 ulp ~ 2e-5) whose summation order differs between sgemm and FFMA;
+  * gradients: max-abs error <= 2e-3 of the gradient's max-abs (atomic order).
+"""
+import pytest
+import torch
+
+from oracle import nice_oracle as O
+from tests import helpers as T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OUT_TOL = dict(rtol=1e-3, atol=3e-4)
+GRAD_REL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def g():
+    return T.load_nice()
+
+
+@pytest.fixture(scope="module")
+def scene(g):
+    return T.cuda_nice(g, DEV)
+
+
+def test_eval_points_stages(g, scene):
+    model, grids, renderer = scene
+    for stage in O.STAGES:
+        for key, pts in ((f"raw_{stage}", g["points"]), (f"raw32_{stage}", g["points"].float())):
+            with torch.no_grad():
+                out = renderer.eval_points(pts.to(DEV), model, grids, stage, DEV).cpu()
+            ref = g[key]
+            assert torch.equal(out[:, 3] == 100, ref[:, 3] == 100), f"{key}: out-of-bound mask differs"
+            torch.testing.assert_close(out, ref, **OUT_TOL, msg=lambda m: f"{key}: {m}")
+
+
+def test_eval_points_contiguous_grids_match_channels_last(g, scene):
+    model, grids, renderer = scene
+    _, grids_nc, _ = T.cuda_nice(g, DEV, channels_last=False)
+    p = g["points"].to(DEV)
+    with torch.no_grad():
+        a = renderer.eval_points(p, model, grids, "color", DEV)
+        b = renderer.eval_points(p, model, grids_nc, "color", DEV)
+    assert torch.equal(a, b)
+
+
+def test_decoder_modules_direct(g, scene):
+    """NICE.forward / sub-decoder forward (no bound override), decoder.py:312-342."""
+    model, grids, _ = scene
+    sd = T.state_dict(g)
+    cpu_grids = {k: g[k] for k in O.GRID_KEYS}
+    bounds = O.decoder_bounds(g["bound"])
+    p = g["points"][:1500]
+    with torch.no_grad():
+        ref = O.nice_forward(sd, p.clone(), cpu_grids, bounds, "color")
+        out = model(p.to(DEV)[None], grids, stage="color").cpu()
+        torch.testing.assert_close(out, ref, **OUT_TOL)
+        ref_mid = O.middle_occ(sd, p.clone(), cpu_grids, bounds)
+        out_mid = model.middle_decoder(p.to(DEV)[None], grids).cpu()
+        torch.testing.assert_close(out_mid, ref_mid, **OUT_TOL)
+        ref_fine = O.fine_occ(sd, p.clone(), cpu_grids, bounds)
+        out_fine = model.fine_decoder(p.to(DEV)[None], grids).cpu()
+        torch.testing.assert_close(out_fine, ref_fine, **OUT_TOL)
+        ref_c = O.coarse_mlp(sd, "coarse_decoder.", O.trilinear_feature(p.clone(), cpu_grids["grid_coarse"], bounds["coarse"]))
+        out_c = model.coarse_decoder(p.to(DEV)[None], grids).cpu()
+        torch.testing.assert_close(out_c, ref_c, **OUT_TOL)
+
+
+def _rays(g, cam):
+    import pointnerf_slam_b200 as P
+    H, W, fx, fy, cx, cy = [float(v) for v in g["intr"]]
+    H0, H1, W0, W1 = [int(v) for v in g["crop"]]
+    c2w = P.get_camera_from_tensor(cam)
+    return P.get_samples(H0, H1, W0, W1, g["indices"].numel(), int(H), int(W), fx, fy, cx, cy, c2w,
+                         g["depth_img"].to(DEV), g["color_img"].to(DEV), DEV, indices=g["indices"].to(DEV))
+
+
+def test_pose_rays_and_gathers_bit_exact(g):
+    import pointnerf_slam_b200 as P
+    cam = g["cam"].to(DEV)
+    c2w = P.get_camera_from_tensor(cam)
+    assert torch.equal(c2w.cpu(), O.camera_from_tensor(g["cam"]))
+    ro, rd, gd, gc = _rays(g, cam)
+    assert torch.equal(ro.cpu(), g["rays_o"]) and torch.equal(rd.cpu(), g["rays_d"])
+    assert torch.equal(gd.cpu(), g["gt_depth"]) and torch.equal(gc.cpu(), g["gt_color"])
+    H, W, fx, fy, cx, cy = [float(v) for v in g["intr"]]
+    ro_f, rd_f = P.get_rays(int(H), int(W), fx, fy, cx, cy, c2w, DEV)
+    ro_r, rd_r = O.get_rays(int(H), int(W), fx, fy, cx, cy, O.camera_from_tensor(g["cam"]))
+    assert torch.equal(rd_f.cpu(), rd_r) and torch.equal(ro_f.cpu(), ro_r)
+
+
+def test_pixel_indices_follow_torch_randint():
+    """The draw is torch.randint on the device, as src/common.py:99 does."""
+    import pointnerf_slam_b200 as P
+    depth = torch.rand(68, 120, device=DEV)
+    color = torch.rand(68, 120, 3, device=DEV)
+    c2w = torch.eye(4, device=DEV)[:3]
+    torch.manual_seed(123)
+    idx = torch.randint(52 * 100, (77,), device=DEV)
+    torch.manual_seed(123)
+    ro, rd, d, c = P.get_samples(8, 60, 10, 110, 77, 68, 120, 60., 60., 59.5, 33.5, c2w, depth, color, DEV)
+    assert torch.equal(d, depth[8:60, 10:110].reshape(-1)[idx])
+    assert torch.equal(c, color[8:60, 10:110].reshape(-1, 3)[idx])
+
+
+def test_z_values_bit_exact(g, scene):
+    _, _, renderer = scene
+    sc = T.oracle_scene(g)
+    for gt in (g["gt_depth"], None):
+        z = renderer.sample_z(g["rays_d"].to(DEV), g["rays_o"].to(DEV), gt.to(DEV) if gt is not None else None).cpu()
+        ref = O.ray_z_values(sc, g["rays_o"], g["rays_d"], gt)
+        assert z.dtype == ref.dtype == torch.float64
+        assert torch.equal(z, ref)
+    # origin outside the bound: far clamps to 0, descending stratified list, still sorted identically
+    ro = g["rays_o"].clone(); ro[:, 0] += 5.0
+    z = renderer.sample_z(g["rays_d"].to(DEV), ro.to(DEV), g["gt_depth"].to(DEV)).cpu()
+    assert torch.equal(z, O.ray_z_values(sc, ro, g["rays_d"], g["gt_depth"]))
+
+
+@pytest.mark.parametrize("stage", ["coarse", "middle", "fine", "color"])
+def test_render_forward_vs_golden(g, scene, stage):
+    model, grids, renderer = scene
+    gt = None if stage == "coarse" else g["gt_depth"].to(DEV)
+    with torch.no_grad():
+        d, v, c = renderer.render_batch_ray(grids, model, g["rays_d"].to(DEV), g["rays_o"].to(DEV), DEV, stage, gt_depth=gt)
+    assert d.dtype == torch.float64 and v.dtype == torch.float64 and c.dtype == torch.float32
+    torch.testing.assert_close(d.cpu(), g[f"{stage}/map/depth"], **OUT_TOL)
+    torch.testing.assert_close(v.cpu(), g[f"{stage}/map/var"], rtol=2e-3, atol=3e-4)
+    torch.testing.assert_close(c.cpu(), g[f"{stage}/map/color"], **OUT_TOL)
+
+
+def test_render_edge_cases(g, scene):
+    model, grids, renderer = scene
+    rd, ro = g["rays_d"].to(DEV), g["rays_o"].to(DEV)
+    with torch.no_grad():
+        d, v, c = renderer.render_batch_ray(grids, model, rd, ro, DEV, "color", gt_depth=None)
+        torch.testing.assert_close(d.cpu(), g["color/nodepth/depth"], **OUT_TOL)
+        torch.testing.assert_close(c.cpu(), g["color/nodepth/color"], **OUT_TOL)
+        ro2 = ro.clone(); ro2[:, 0] += 5.0
+        d, v, c = renderer.render_batch_ray(grids, model, rd, ro2, DEV, "color", gt_depth=g["gt_depth"].to(DEV))
+        assert torch.isfinite(d).all()
+        torch.testing.assert_close(d.cpu(), g["color/outside/depth"], **OUT_TOL)
+        torch.testing.assert_close(c.cpu(), g["color/outside/color"], **OUT_TOL)
+        # empty batch
+        d, v, c = renderer.render_batch_ray(grids, model, rd[:0], ro[:0], DEV, "color", gt_depth=g["gt_depth"].to(DEV)[:0])
+        assert d.shape == (0,) and c.shape == (0, 3)
+
+
+@pytest.mark.parametrize("stage", ["coarse", "middle", "fine", "color"])
+def test_mapping_gradients_vs_golden(g, stage):
+    """Mapper.py:628-662 iteration: grads into grids and decoder parameters."""
+    model, grids, renderer = T.cuda_nice(g, DEV)
+    for k in grids:
+        grids[k].requires_grad_(True)
+    gt = None if stage == "coarse" else g["gt_depth"].to(DEV)
+    d, v, c = renderer.render_batch_ray(grids, model, g["rays_d"].to(DEV), g["rays_o"].to(DEV), DEV, stage, gt_depth=gt)
+    gtd = g["gt_depth"].to(DEV) if gt is not None else torch.ones_like(g["gt_depth"]).to(DEV)
+    loss = O.mapping_loss(d, c, gtd, g["gt_color"].to(DEV), stage)
+    torch.testing.assert_close(loss.cpu(), g[f"{stage}/map/loss"], rtol=1e-3, atol=1e-3)
+    loss.backward()
+    for k in O.GRID_KEYS:
+        key = f"{stage}/map/grad_{k}"
+        if key in g:
+            assert grids[k].grad is not None, key
+            assert T.rel_max(grids[k].grad, g[key]) < GRAD_REL, key
+        else:
+            assert grids[k].grad is None or float(grids[k].grad.abs().max()) == 0.0, f"{k} must get no gradient in {stage}"
+    checked = 0
+    for name, p in model.named_parameters():
+        key = f"{stage}/map/gradsd/{name}"
+        if key in g:
+            assert p.grad is not None, key
+            assert T.rel_max(p.grad, g[key]) < GRAD_REL, key
+            checked += 1
+        else:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+    assert checked > 0
+    if stage == "color":  # 4th output row of the colour decoder is overwritten => zero gradient
+        assert float(model.color_decoder.output_linear.weight.grad[3].abs().max()) == 0.0
+
+
+def test_tracking_gradient_to_camera(g, scene):
+    """Tracker.py:269-335 iteration: grads to the camera 7-vector only."""
+    model, grids, renderer = scene
+    renderer.freeze_map = True
+    try:
+        cam = g["cam"].to(DEV).requires_grad_(True)
+        ro, rd, gd, gc = _rays(g, cam)
+        d, v, c = renderer.render_batch_ray(grids, model, rd, ro, DEV, "color", gt_depth=gd)
+        loss = O.tracking_loss(d, v, c, gd, gc)
+        loss.backward()
+    finally:
+        renderer.freeze_map = False
+    torch.testing.assert_close(loss.cpu(), g["color/track/loss"], rtol=2e-3, atol=1e-3)
+    assert T.rel_max(cam.grad, g["color/track/grad_cam"]) < 5e-3
+    assert all(p.grad is None for p in model.parameters())
+
+
+def test_ray_shards_sum_to_full_gradient(g):
+    """Losses are plain sums, so summed shard gradients equal the un-sharded
+    gradient when the batch-global max depth is shared."""
+    model, grids, renderer = T.cuda_nice(g, DEV)
+    for k in grids:
+        grids[k].requires_grad_(True)
+    rd, ro, gd, gc = g["rays_d"].to(DEV), g["rays_o"].to(DEV), g["gt_depth"].to(DEV), g["gt_color"].to(DEV)
+    d, v, c = renderer.render_batch_ray(grids, model, rd, ro, DEV, "color", gt_depth=gd)
+    O.mapping_loss(d, c, gd, gc, "color").backward()
+    full = {k: grids[k].grad.clone() for k in grids if grids[k].grad is not None}
+    for k in grids:
+        grids[k].grad = None
+    renderer.depth_max_override = gd.max().reshape(1)
+    try:
+        for sl in (slice(0, 40), slice(40, 96)):
+            d, v, c = renderer.render_batch_ray(grids, model, rd[sl], ro[sl], DEV, "color", gt_depth=gd[sl])
+            O.mapping_loss(d, c, gd[sl], gc[sl], "color").backward()
+    finally:
+        renderer.depth_max_override = None
+    for k, f in full.items():
+        assert T.rel_max(grids[k].grad, f) < 1e-5, k
+
+
+def test_composite_standalone_matches_oracle(g):
+    import pointnerf_slam_b200 as P
+    torch.manual_seed(0)
+    R, S = 50, 48
+    raw = torch.randn(R, S, 4)
+    z = torch.sort(torch.rand(R, S, dtype=torch.float64) * 3, -1)[0]
+    rd = torch.randn(R, 3)
+    for occ in (True, False):
+        rr = raw.clone().requires_grad_(True)
+        d, v, c, w = O.composite(rr, z, rd, occ)
+        (d.sum() + 0.3 * v.sum() + (c * torch.tensor([1.0, -2.0, 0.5])).sum()).backward()
+        rc = raw.clone().to(DEV).requires_grad_(True)
+        d2, v2, c2, w2 = P.raw2outputs_nerf_color(rc, z.to(DEV), rd.to(DEV), occupancy=occ, device=DEV)
+        (d2.sum() + 0.3 * v2.sum() + (c2 * torch.tensor([1.0, -2.0, 0.5], device=DEV)).sum()).backward()
+        torch.testing.assert_close(d2.cpu(), d.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(v2.cpu(), v.detach(), rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(c2.cpu(), c.detach(), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(w2.cpu(), w.detach(), rtol=1e-4, atol=1e-7)
+        assert T.rel_max(rc.grad, rr.grad) < 1e-4
