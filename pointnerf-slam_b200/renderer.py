@@ -238,6 +238,9 @@ class Renderer(object):
         """depth (N,) f64, uncertainty (N,) f64, colour (N,3) f32 (Renderer.py:63-203)."""
         plan = self._plan(decoders, stage)
         dev = rays_o.device
+        if rays_o.shape[0] == 0:  # empty batch: nothing to launch
+            return (torch.zeros(0, dtype=torch.float64, device=dev), torch.zeros(0, dtype=torch.float64, device=dev),
+                    torch.zeros((0, 3), dtype=torch.float32, device=dev))
         cfg = _RayCfg(self.N_samples, self.N_surface, self.N_importance, bool(self.lindisp), float(self.perturb),
                       bool(self.occupancy), self.bound, bool(self.freeze_map), self._constants(dev))
         t_rand = None
