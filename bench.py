@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the differentiable ray-rendering hot path (BASELINE.json metric:
+rays/sec forward+backward ``render_batch_ray``; % of the HBM roofline; vs the CPU
+reference).
+
+Workload (BASELINE.json configs[2]) -- one NICE-SLAM mapping
+iteration, stage ``color``, on a synthetic Replica-room0-shaped scene:
+5 keyframes x 1000 pixels = 5000 rays x 48 samples per rank; pixel sampling and
+ray generation from the (bundle-adjusted) camera tensors, ``render_batch_ray``,
+the Mapper loss (src/Mapper.py:628-646) and the backward into the middle / fine /
+colour grids, the colour decoder and 4 camera poses (src/Mapper.py:402-477
+upstream configuration: fix_fine, BA).  The optimiser step is not part of the
+metric and is outside the timed region in both arms.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL): rays shard across ranks
+(weak scaling: 5000 rays per rank), the batch-global depth maximum is shared by
+an all-reduce(MAX) and the gradients by an all-reduce(SUM) inside the timed step.
+
+``--impl reference`` times the reference's own torch implementation of the same
+step on the host cores (the oracle port, pinned bit-equal against the reference;
+the reference is pure Python and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = {"rendering": {"lindisp": False, "perturb": 0.0, "N_samples": 32, "N_surface": 16, "N_importance": 0},
+       "scale": 1, "occupancy": True, "coarse": True, "data": {"dim": 3},
+       "grid_len": {"coarse": 2, "middle": 0.32, "fine": 0.16, "color": 0.16, "bound_divisible": 0.32},
+       "model": {"c_dim": 32, "coarse_bound_enlarge": 2, "pos_embedding_method": "fourier"},
+       "mapping": {"bound": [[-2.9, 8.9], [-3.2, 5.5], [-3.5, 3.3]]}}
+H, W, FX, FY, CX, CY = 680, 1200, 600.0, 600.0, 599.5, 339.5
+N_KEYFRAMES, PIX_PER_KF, S = 5, 1000, 48
+W_COLOR = 0.2
+# algorithmic bytes per ray, fwd+bwd mapping, stage colour
+BYTES_PER_RAY_STEP = 589_872
+BYTES_PER_SAMPLE_GATHER = 1024      # 8 corners x 32 ch x 4 B per grid
+WORKLOAD = "nice_mapping_iter_color: 5 keyframes x 1000 px, 48 samples/ray, room0 grids, BA"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def synthetic_frames(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    frames = []
+    for _ in range(n):
+        depth = 1.0 + 2.0 * torch.rand(H, W, generator=g)
+        depth[torch.rand(H, W, generator=g) < 0.02] = 0.0
+        frames.append((depth, torch.rand(H, W, 3, generator=g)))
+    return frames
+
+
+def keyframe_poses(rank):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "room0_poses.npz"))
+    c2w = torch.from_numpy(z["c2w"]).float()
+    sel = [(rank * N_KEYFRAMES + k) * 5 % c2w.shape[0] for k in range(N_KEYFRAMES)]
+    return c2w[sel]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# ours
+# ----------------------------------------------------------------------------
+def run_ours(args):
+    import pointnerf_slam_b200 as P
+    from pointnerf_slam_b200 import _lib as L
+    from pointnerf_slam_b200 import dist as D
+    import torch.distributed as dist
+
+    rank, world, local = D.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    bound = P.load_bound(CFG)
+    torch.manual_seed(0)
+    model = P.get_model(CFG, nice=True).to(dev)
+    P.attach_bounds(model, bound)
+    grids = P.grid_init(CFG, bound, dev, generator=torch.Generator().manual_seed(1))
+    slam = types.SimpleNamespace(bound=bound, H=H, W=W, fx=FX, fy=FY, cx=CX, cy=CY, nice=True)
+    renderer = P.Renderer(CFG, None, slam)
+    # mapping configuration: grids + colour decoder trained, fine/middle/coarse decoders fixed, BA on 4 of 5 poses
+    for k in ("grid_middle", "grid_fine", "grid_color"):
+        grids[k].requires_grad_(True)
+    for name, p in model.named_parameters():
+        p.requires_grad_(name.startswith("color_decoder."))
+    frames_host = synthetic_frames(N_KEYFRAMES, 100 + rank)
+    frames = [(d.to(dev), c.to(dev)) for d, c in frames_host]
+    poses = keyframe_poses(rank).to(dev)
+    cams = [P.get_tensor_from_camera(poses[k]).to(dev).requires_grad_(k > 0) for k in range(N_KEYFRAMES)]
+    trained = [grids[k] for k in ("grid_middle", "grid_fine", "grid_color")] + \
+              [p for p in model.parameters() if p.requires_grad] + cams[1:]
+    pinned_depth = frames_host[0][0].pin_memory()
+    pinned_color = frames_host[0][1].pin_memory()
+    pinned_poses = poses.cpu().pin_memory()
+    poses_dev = torch.empty_like(poses)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(e2e=False):
+        if e2e:  # host -> device copy of this step's inputs from pinned memory
+            frames[0][0].copy_(pinned_depth, non_blocking=True)
+            frames[0][1].copy_(pinned_color, non_blocking=True)
+            poses_dev.copy_(pinned_poses, non_blocking=True)
+        ro, rd, gd, gc = [], [], [], []
+        for k in range(N_KEYFRAMES):
+            c2w = P.get_camera_from_tensor(cams[k])
+            idx = torch.randint(H * W, (PIX_PER_KF,), device=dev, generator=gen)
+            o, d, dd, cc = P.get_samples(0, H, 0, W, PIX_PER_KF, H, W, FX, FY, CX, CY, c2w, frames[k][0], frames[k][1], dev,
+                                         indices=idx)
+            ro.append(o); rd.append(d); gd.append(dd); gc.append(cc)
+        ro, rd, gd, gc = torch.cat(ro), torch.cat(rd), torch.cat(gd), torch.cat(gc)
+        renderer.depth_max_override = D.share_depth_max(gd) if world > 1 else None
+        depth, var, color = renderer.render_batch_ray(grids, model, rd, ro, dev, "color", gt_depth=gd)
+        m = gd > 0
+        loss = torch.abs(gd[m] - depth[m]).sum() + W_COLOR * torch.abs(gc - color).sum()
+        loss.backward()
+        D.allreduce_gradients([t.grad for t in trained])
+        out = loss.item() if e2e else None  # device -> host read of the step's result
+        for t in trained:
+            t.grad = None
+        return out
+
+    def timed(k, e2e, profile):
+        L.PROFILE = {} if profile else None
+        evs = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        n0 = L.lib().pn_launch_count()
+        wall0 = time.perf_counter()
+        for _ in range(k):
+            flush.fill_(1)      # evict L2 between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(e2e)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        prof = L.PROFILE
+        L.PROFILE = None
+        return t.item(), L.lib().pn_launch_count() - n0, prof, wall
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches, prof, _ = timed(args.steps, False, True)
+    clocks = sampler.stop() if rank == 0 else None
+    if args.light:
+        ms_e2e = ms_total
+    else:
+        for _ in range(2):
+            step(True)
+        ms_e2e, _, _, _ = timed(args.steps, True, False)
+
+    rays_per_step = N_KEYFRAMES * PIX_PER_KF * world
+    value = rays_per_step * args.steps / (ms_total * 1e-3)
+    e2e_value = rays_per_step * args.steps / (ms_e2e * 1e-3)
+    hbm, which = peaks()
+    # dominant kernel: largest total event time among the profiled C-ABI calls
+    kern = {k: [a.elapsed_time(b) for a, b in v] for k, v in (prof or {}).items()}
+    share = {k: sum(v) / ms_total for k, v in kern.items()}
+    top = max(kern, key=lambda k: sum(kern[k])) if kern else None
+    n_samples = N_KEYFRAMES * PIX_PER_KF * S
+    # algorithmic bytes per launch of each decoder kernel (DESIGN.md "roofline"): gathers of 1024 B
+    # per sample per grid read, plus 2048 B per sample read-modify-write of the gradient grid in backward
+    alg = {"grid_mlp_fwd:color": 1, "grid_mlp_fwd:fine": 2, "grid_mlp_fwd:middle": 1,
+           "grid_mlp_bwd:color": 3, "grid_mlp_bwd:fine": 3, "grid_mlp_bwd:middle": 3}
+    roofline = None
+    if top is not None:
+        dur_ms = statistics.mean(kern[top])
+        bytes_launch = n_samples * BYTES_PER_SAMPLE_GATHER * alg.get(top, 1)
+        achieved = bytes_launch / (dur_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
+                    "frac": round(achieved / hbm, 4), "traffic": None, "peak_source": which,
+                    "avg_launch_ms": round(dur_ms, 4), "alg_bytes_per_launch": bytes_launch,
+                    "kernel_share_of_step": {k: round(v, 3) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
+                    "note": "kernel is FP32-FFMA bound (25 FLOP/B); HBM roofline is the BASELINE.md denominator"}
+    step_frac = value / world * BYTES_PER_RAY_STEP / (hbm * 1e9)
+    line = {"metric": "rays/sec fwd+bwd render_batch_ray (NICE mapping iteration, stage color)", "value": round(value, 1),
+            "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N_KEYFRAMES * PIX_PER_KF, "samples_per_ray": S,
+                       "grids": {k: list(v.shape) for k, v in grids.items()}, "l2": "flushed between timed iterations "
+                       "(256 MiB fill, untimed); per-step CUDA events summed", "parallelism": f"ray-shard dp{world}"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "rays/s",
+                    "h2d_bytes_per_step": pinned_depth.numel() * 4 + pinned_color.numel() * 4 + pinned_poses.numel() * 4,
+                    "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 4)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "roofline_step": {"bytes_per_ray": BYTES_PER_RAY_STEP, "frac_of_hbm_per_gpu": round(step_frac, 4),
+                              "peak": hbm, "peak_source": which}}
+    if rank == 0 and world == 1 and not args.light:
+        line["cpu_baseline"] = cpu_baseline(sample_kf_pixels=200, iters=2)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ----------------------------------------------------------------------------
+def oracle_mapping_setup(pix_per_kf, seed=0):
+    from oracle import nice_oracle as O
+    bound = O.scene_bound(CFG["mapping"]["bound"], 1.0, 0.32)
+    sd = O.init_nice_state(seed=seed)
+    grids = O.init_grids(bound, CFG["grid_len"], 32, 2, True, torch.Generator().manual_seed(1))
+    frames = synthetic_frames(N_KEYFRAMES, 100)
+    poses = keyframe_poses(0)
+    return O, bound, sd, grids, frames, poses
+
+
+def oracle_mapping_step(O, bound, sd, grids, frames, poses, pix_per_kf, gen):
+    g = {k: v.clone().requires_grad_(k != "grid_coarse") for k, v in grids.items()}
+    s = {k: v.clone().requires_grad_(k.startswith("color_decoder.")) for k, v in sd.items()}
+    cams = [poses[k][:3].clone().requires_grad_(k > 0) for k in range(N_KEYFRAMES)]
+    ro, rd, gd, gc = [], [], [], []
+    for k in range(N_KEYFRAMES):
+        idx = torch.randint(H * W, (pix_per_kf,), generator=gen)
+        o, d, dd, cc, _ = O.get_samples(0, H, 0, W, pix_per_kf, FX, FY, CX, CY, cams[k], frames[k][0], frames[k][1], idx)
+        ro.append(o); rd.append(d); gd.append(dd); gc.append(cc)
+    ro, rd, gd, gc = torch.cat(ro), torch.cat(rd), torch.cat(gd), torch.cat(gc)
+    scene = O.Scene(s, g, bound, nice=True, occupancy=True)
+    depth, var, color = O.render_batch_ray(scene, rd, ro, "color", gd)
+    loss = O.mapping_loss(depth, color, gd, gc, "color", W_COLOR)
+    loss.backward()
+    return loss.item()
+
+
+def cpu_baseline(sample_kf_pixels=200, iters=2):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, bound, sd, grids, frames, poses = oracle_mapping_setup(sample_kf_pixels)
+    gen = torch.Generator().manual_seed(5)
+    oracle_mapping_step(O, bound, sd, grids, frames, poses, sample_kf_pixels, gen)  # warm-up
+    best = float("inf")
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        oracle_mapping_step(O, bound, sd, grids, frames, poses, sample_kf_pixels, gen)
+        best = min(best, time.perf_counter() - t0)
+    rays = N_KEYFRAMES * sample_kf_pixels
+    return {"value": round(rays / best, 1), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"same mapping iteration on {N_KEYFRAMES} x {sample_kf_pixels} px = {rays} rays, torch CPU, "
+                      f"best of {iters} after 1 warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pix = 200   # bounded sample: 5 x 200 px per step (the reference's own Replica default, Mapper.py:397)
+    O, bound, sd, grids, frames, poses = oracle_mapping_setup(pix)
+    gen = torch.Generator().manual_seed(5)
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle_mapping_step(O, bound, sd, grids, frames, poses, pix, gen)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_mapping_step(O, bound, sd, grids, frames, poses, pix, gen)
+    dt = time.perf_counter() - t0
+    rays = N_KEYFRAMES * pix
+    value = rays * steps / dt
+    sample = f"{N_KEYFRAMES} x {pix} px = {rays} rays per step, {steps} steps, torch CPU ({torch.get_num_threads()} threads)"
+    line = {"impl": "reference", "metric": "rays/sec fwd+bwd render_batch_ray (NICE mapping iteration, stage color)",
+            "value": round(value, 1), "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+            "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "oracle port of the reference's torch path (pinned bit-equal), host cores"},
+            "cpu_baseline": {"value": round(value, 1), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": round(value, 1), "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--light", action="store_true", help="profiling runs: skip the e2e pass and the CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

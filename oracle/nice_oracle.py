@@ -191,8 +191,9 @@ def get_samples(H0, H1, W0, W1, n, fx, fy, cx, cy, c2w, depth, color,
     ``torch.randint`` exactly like src/common.py:99.  Returns
     (rays_o, rays_d, depth, color, indices); src/common.py:92-134."""
     i, j = pixel_lattice(H0, H1, W0, W1)
+    i, j = i.to(depth.device), j.to(depth.device)
     if indices is None:
-        indices = torch.randint(i.shape[0], (n,))
+        indices = torch.randint(i.shape[0], (n,), device=depth.device)
     indices = indices.clamp(0, i.shape[0])
     d = depth[H0:H1, W0:W1].reshape(-1)[indices]
     c = color[H0:H1, W0:W1].reshape(-1, 3)[indices]
@@ -203,7 +204,7 @@ def get_samples(H0, H1, W0, W1, n, fx, fy, cx, cy, c2w, depth, color,
 def get_rays(H, W, fx, fy, cx, cy, c2w) -> Tuple[Tensor, Tensor]:
     """All rays of an image, (H,W,3) each; src/common.py:248-266."""
     i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
-    i, j = i.t(), j.t()
+    i, j = i.t().to(c2w.device), j.t().to(c2w.device)
     dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1).reshape(H, W, 1, 3)
     rays_d = torch.sum(dirs * c2w[:3, :3], -1)
     return c2w[:3, -1].expand(rays_d.shape), rays_d
@@ -281,15 +282,15 @@ def nice_forward(sd: Mapping[str, Tensor], p: Tensor, grids: Mapping[str, Tensor
     src/conv_onet/models/decoder.py:312-342."""
     if stage == "coarse":
         occ = coarse_mlp(sd, "coarse_decoder.", trilinear_feature(p, grids["grid_coarse"], bounds["coarse"]))
-        raw = torch.zeros(occ.shape[0], 4)
+        raw = torch.zeros(occ.shape[0], 4, device=occ.device)
         raw[..., -1] = occ
     elif stage == "middle":
         occ = middle_occ(sd, p, grids, bounds)
-        raw = torch.zeros(occ.shape[0], 4)
+        raw = torch.zeros(occ.shape[0], 4, device=occ.device)
         raw[..., -1] = occ
     elif stage == "fine":
         f = fine_occ(sd, p, grids, bounds)
-        raw = torch.zeros(f.shape[0], 4)
+        raw = torch.zeros(f.shape[0], 4, device=f.device)
         raw[..., -1] = f + middle_occ(sd, p, grids, bounds)
     elif stage == "color":
         f = fine_occ(sd, p, grids, bounds)
@@ -351,7 +352,7 @@ def composite(raw: Tensor, z_vals: Tensor, rays_d: Tensor, occupancy: bool):
         alpha = torch.sigmoid(10 * raw[..., -1])
     else:
         alpha = 1.0 - torch.exp(-F.relu(raw[..., -1]) * dists)
-    ones = torch.ones((alpha.shape[0], 1))
+    ones = torch.ones((alpha.shape[0], 1), device=alpha.device)
     trans = torch.cumprod(torch.cat([ones, (1.0 - alpha + 1e-10).float()], -1).float(), -1)[:, :-1]
     weights = alpha.float() * trans
     rgb_map = torch.sum(weights[..., None] * rgb, -2)
@@ -372,7 +373,7 @@ def sample_pdf(bins: Tensor, weights: Tensor, n: int, det: bool = True, u: Optio
             u = torch.linspace(0.0, 1.0, steps=n).expand(list(cdf.shape[:-1]) + [n])
         else:
             u = torch.rand(list(cdf.shape[:-1]) + [n])
-    u = u.contiguous()
+    u = u.to(cdf.device).contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = torch.clamp(inds - 1, min=0)
     above = torch.clamp(inds, max=cdf.shape[-1] - 1)
@@ -399,21 +400,21 @@ def ray_z_values(scene: Scene, rays_o: Tensor, rays_d: Tensor, gt_depth: Optiona
     with torch.no_grad():
         o = rays_o.clone().detach().unsqueeze(-1)
         d = rays_d.clone().detach().unsqueeze(-1)
-        t = (scene.bound.unsqueeze(0) - o) / d
+        t = (scene.bound.unsqueeze(0).to(o.device) - o) / d
         far_bb = torch.min(torch.max(t, dim=2)[0], dim=1)[0].unsqueeze(-1)
         far_bb += 0.01
     far = torch.clamp(far_bb, 0, (gt_depth * 1.2).max()) if gt_depth is not None else far_bb
     z_surface = None
     if n_surface > 0:
         has = gt_depth > 0
-        ts = torch.linspace(0.0, 1.0, steps=n_surface).double()
+        ts = torch.linspace(0.0, 1.0, steps=n_surface).double().to(rays_o.device)
         g = gt_depth[has].unsqueeze(-1).repeat(1, n_surface)
         near_surface = 0.95 * g * (1.0 - ts) + 1.05 * g * ts
-        z_surface = torch.zeros(gt_depth.shape[0], n_surface).double()
+        z_surface = torch.zeros(gt_depth.shape[0], n_surface).to(rays_o.device).double()
         has = has.squeeze(-1)
         z_surface[has, :] = near_surface
         z_surface[~has, :] = 0.001 * (1.0 - ts) + torch.max(gt_depth) * ts
-    tv = torch.linspace(0.0, 1.0, steps=n_samples)
+    tv = torch.linspace(0.0, 1.0, steps=n_samples).to(rays_o.device)
     if not scene.lindisp:
         z = near * (1.0 - tv) + far * tv
     else:
@@ -424,7 +425,7 @@ def ray_z_values(scene: Scene, rays_o: Tensor, rays_d: Tensor, gt_depth: Optiona
         lower = torch.cat([z[..., :1], mids], -1)
         if t_rand is None:
             t_rand = torch.rand(z.shape)
-        z = lower + (upper - lower) * t_rand
+        z = lower + (upper - lower) * t_rand.to(z.device)
     if n_surface > 0:
         z, _ = torch.sort(torch.cat([z, z_surface.double()], -1), -1)
     return z
@@ -469,14 +470,14 @@ def regulation(scene: Scene, rays_d: Tensor, rays_o: Tensor, gt_depth: Tensor, s
                t_rand: Optional[Tensor] = None) -> Tensor:
     """Densities of jittered samples in [0, 0.85*depth]; src/utils/Renderer.py:263-301."""
     g = gt_depth.reshape(-1, 1).repeat(1, scene.n_samples)
-    tv = torch.linspace(0.0, 1.0, steps=scene.n_samples)
+    tv = torch.linspace(0.0, 1.0, steps=scene.n_samples).to(rays_o.device)
     z = 0.0 * (1.0 - tv) + (g * 0.85) * tv
     mids = 0.5 * (z[..., 1:] + z[..., :-1])
     upper = torch.cat([mids, z[..., -1:]], -1)
     lower = torch.cat([z[..., :1], mids], -1)
     if t_rand is None:
         t_rand = torch.rand(z.shape)
-    z = lower + (upper - lower) * t_rand
+    z = lower + (upper - lower) * t_rand.to(z.device)
     pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
     return eval_points(scene, pts.reshape(-1, 3), stage)[:, -1]
 

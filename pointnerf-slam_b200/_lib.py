@@ -73,12 +73,39 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.pn_last_error.restype = C.c_char_p
         _lib.pn_version.restype = C.c_int
+        _lib.pn_launch_count.restype = C.c_longlong
     return _lib
+
+
+# Optional per-kernel timing for bench.py: when PROFILE is a dict, every checked
+# C-ABI call is bracketed by CUDA events on the current stream and the pairs are
+# appended under the call's name.  None (default) = no events.
+PROFILE = None
 
 
 def check(status: int, what: str) -> None:
     if status != 0:
         raise RuntimeError(f"{what} failed: {lib().pn_last_error().decode()}")
+
+
+class timed:
+    """with timed('name', device): ... records an event pair when PROFILE is on."""
+
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream(self.device))
+            PROFILE.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

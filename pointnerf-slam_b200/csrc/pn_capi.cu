@@ -7,6 +7,7 @@
 namespace pn {
 namespace {
 thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;  // kernels launched by this thread through the C ABI
 }
 
 void set_error(const char* fmt, ...) {
@@ -18,6 +19,7 @@ void set_error(const char* fmt, ...) {
 
 int launch_status(const char* what) {
   const cudaError_t e = cudaGetLastError();
+  ++g_launches;
   if (e == cudaSuccess) return 0;
   set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
   return 1;
@@ -34,3 +36,4 @@ int sm_count() {
 
 extern "C" const char* pn_last_error(void) { return pn::g_err; }
 extern "C" int pn_version(void) { return 100; }
+extern "C" long long pn_launch_count(void) { return pn::g_launches; }

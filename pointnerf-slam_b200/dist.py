@@ -1,0 +1,103 @@
+"""Data-parallel mapping over the GPUs of one box.
+
+One process per GPU.  Rays shard across ranks with no data-path collective;
+grids, decoders and poses are replicated.  Two exchanges per iteration:
+
+  * ``share_depth_max``   all-reduce(MAX) of one float: ``render_batch_ray``
+    couples all rays of a batch through ``max(gt_depth)``
+    (src/utils/Renderer.py:112,149), so the batch-global value must be shared
+    before the z-values are placed;
+  * ``allreduce_gradients`` all-reduce(SUM) of grid, decoder and pose
+    gradients.  The reference's losses are plain sums (src/Mapper.py:641-646),
+    so summed shard gradients equal the single-GPU gradient -- no rescaling.
+
+The collectives run on ``torch.distributed`` (NCCL over NVLink on the GPU box,
+gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from torchrun's environment; initialises
+    the default process group when world_size > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of n units for this rank (sizes differ by <= 1)."""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def share_depth_max(gt_depth: torch.Tensor) -> torch.Tensor:
+    """1-element tensor holding max(gt_depth) over every rank's shard."""
+    m = gt_depth.detach().reshape(-1).float().max().reshape(1) if gt_depth.numel() else \
+        torch.full((1,), float("-inf"), device=gt_depth.device)
+    if world_size() > 1:
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    return m
+
+
+def allreduce_gradients(tensors: Iterable[Optional[torch.Tensor]], small_bytes: int = 1 << 20) -> None:
+    """In-place SUM all-reduce of gradient tensors.  Large tensors (the feature
+    grids) go individually; small ones (decoder parameters, poses) are packed
+    into one bucket so that launch latency, not link count, sizes the calls."""
+    if world_size() == 1:
+        return
+    big: List[torch.Tensor] = []
+    small: List[torch.Tensor] = []
+    for t in tensors:
+        if t is None:
+            continue
+        (big if t.numel() * t.element_size() >= small_bytes else small).append(t)
+    works = []
+    copies = []
+    for t in big:
+        # channels-last grid gradients are dense in memory: reduce the storage order as is
+        flat = t.permute(0, 2, 3, 4, 1) if (t.dim() == 5 and not t.is_contiguous()) else t
+        if not flat.is_contiguous():
+            tmp = flat.contiguous()
+            copies.append((flat, tmp))
+            flat = tmp
+        works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+    if small:
+        dtype = small[0].dtype
+        bucket = torch.cat([t.reshape(-1).to(dtype) for t in small])
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+        off = 0
+        for t in small:
+            n = t.numel()
+            t.copy_(bucket[off:off + n].reshape(t.shape))
+            off += n
+    for w in works:
+        w.wait()
+    for dst, tmp in copies:
+        dst.copy_(tmp)
+
+
+def mapping_gradients(params: Sequence[torch.Tensor]) -> List[Optional[torch.Tensor]]:
+    return [p.grad for p in params]

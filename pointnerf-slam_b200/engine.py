@@ -273,8 +273,9 @@ def plan_forward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, dev
             if p.kind == "grid":
                 m = _mlp_struct(p)
                 ga, gb = _pn_grid(grids_cl[p.grid_a]), _pn_grid(grids_cl.get(p.grid_b) if p.grid_b else None)
-                L.check(lib.pn_grid_mlp_fwd(C.byref(ps), C.byref(m), C.byref(ga), _byref(gb), nb, mb, apply_mask,
-                                            p.out_mode, C.c_void_p(raw.data_ptr()), _byref(sst), st), "pn_grid_mlp_fwd")
+                with L.timed(f"grid_mlp_fwd:{p.dec.name}", device):
+                    L.check(lib.pn_grid_mlp_fwd(C.byref(ps), C.byref(m), C.byref(ga), _byref(gb), nb, mb, apply_mask,
+                                                p.out_mode, C.c_void_p(raw.data_ptr()), _byref(sst), st), "pn_grid_mlp_fwd")
             elif p.kind == "coarse":
                 m = _coarse_struct(p)
                 ga = _pn_grid(grids_cl[p.grid_a])
@@ -322,9 +323,10 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
             if p.kind == "grid":
                 m = _mlp_struct(p)
                 ga, gb = _pn_grid(grids_cl[p.grid_a]), _pn_grid(grids_cl.get(p.grid_b) if p.grid_b else None)
-                L.check(lib.pn_grid_mlp_bwd(C.byref(ps), C.byref(m), C.byref(ga), _byref(gb), nb, mb, apply_mask,
-                                            C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
-                                            C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_grid_mlp_bwd")
+                with L.timed(f"grid_mlp_bwd:{p.dec.name}", device):
+                    L.check(lib.pn_grid_mlp_bwd(C.byref(ps), C.byref(m), C.byref(ga), _byref(gb), nb, mb, apply_mask,
+                                                C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
+                                                C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_grid_mlp_bwd")
                 if want_w[i]:
                     gp = [torch.zeros_like(t) for t in p.params]
                     g = L.PnGridMlpGrad()
@@ -333,8 +335,9 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                         g.W[k] = gp[1 + k].data_ptr(); g.b[k] = gp[6 + k].data_ptr()
                         g.Wc[k] = gp[11 + k].data_ptr(); g.bc[k] = gp[16 + k].data_ptr()
                     g.Wo, g.bo = gp[21].data_ptr(), gp[22].data_ptr()
-                    L.check(lib.pn_grid_mlp_wgrad(C.c_int64(n), C.byref(m), C.byref(sst), C.byref(wst), C.byref(g), st),
-                            "pn_grid_mlp_wgrad")
+                    with L.timed(f"grid_mlp_wgrad:{p.dec.name}", device):
+                        L.check(lib.pn_grid_mlp_wgrad(C.c_int64(n), C.byref(m), C.byref(sst), C.byref(wst), C.byref(g), st),
+                                "pn_grid_mlp_wgrad")
                     g_params.append(gp)
                 else:
                     g_params.append(None)
