@@ -206,6 +206,35 @@ int pn_coarse_mlp_bwd(const pn_points* pts, const pn_coarse_mlp* w, const pn_gri
 int pn_coarse_mlp_wgrad(int64_t N, const pn_stash* stash, const pn_wscratch* ws,
                         const pn_coarse_mlp_grad* g, void* stream);
 
+/* iMAP* single MLP = decoder.MLP with c_dim 0 (conv_onet/config.py:28-32): Fourier-93 ->
+ * n_blocks x [hidden] relu layers (no skips) -> 4 outputs.  Activations are row-major:
+ * E (N,96) embedding, H [n_blocks](N,hidden) block outputs (also the relu masks), P32 [3][N]. */
+#define PN_IMAP_MAX_BLOCKS 8
+typedef struct pn_imap_mlp {
+  const float* B;                      /* embedder._B (3,93) */
+  const float* W[PN_IMAP_MAX_BLOCKS];  /* pts_linears.i.weight: (hidden,93), then (hidden,hidden) */
+  const float* b[PN_IMAP_MAX_BLOCKS];
+  const float* Wo;                     /* (4,hidden) */
+  const float* bo;
+  int hidden, n_blocks;
+} pn_imap_mlp;
+typedef struct pn_imap_mlp_grad {      /* accumulated (+=), any pointer may be NULL */
+  float* B;
+  float* W[PN_IMAP_MAX_BLOCKS];
+  float* b[PN_IMAP_MAX_BLOCKS];
+  float* Wo;
+  float* bo;
+} pn_imap_mlp_grad;
+/* raw (N,4) = MLP(p); component 3 forced to 100 outside mask_bound if apply_mask.
+ * E, H are always written (they are the backward's stash); P32 optional. */
+int pn_imap_mlp_fwd(const pn_points* pts, const pn_imap_mlp* w, const double* mask_bound, int apply_mask,
+                    float* raw, float* E, float* H, float* P32, void* stream);
+/* Backward: g_raw (N,4) -> parameter gradients g (optional), g_pts (N,3) += (optional).
+ * GA, GB: scratch (N, max(hidden,96)) each; GO: scratch (N,4). */
+int pn_imap_mlp_bwd(const pn_points* pts, const pn_imap_mlp* w, const double* mask_bound, int apply_mask,
+                    const float* g_raw, const float* E, const float* H, const float* P32, float* GA, float* GB,
+                    float* GO, float* g_pts, const pn_imap_mlp_grad* g, void* stream);
+
 /* -------- compositing (src/common.py:204-245) -------- */
 
 /* raw (R,S,4), z (R,S) f64, rays_d (R,3) -> depth (R) f64, var (R) f64, rgb (R,3) f32,

@@ -60,6 +60,38 @@ class PnWscratch(C.Structure):
 OUT_SET_ALL, OUT_SET_W, OUT_ADD_W = 0, 1, 2
 
 _lib: Optional[C.CDLL] = None
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pnslam.h")
+
+
+def _declare_prototypes(lib: C.CDLL) -> None:
+    """Set ctypes argtypes for every ``int pn_*(...)`` declared in include/pnslam.h so
+    that a call with the wrong number or kind of arguments raises instead of
+    corrupting the stack."""
+    import re
+    if not os.path.exists(HEADER_PATH):
+        return
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER_PATH).read(), flags=re.S)
+    for m in re.finditer(r"\bint\s+(pn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        if not hasattr(lib, name):
+            continue
+        types = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    types.append(C.c_void_p)
+                elif "int64_t" in a:
+                    types.append(C.c_int64)
+                elif a.startswith("float") or " float " in " " + a:
+                    types.append(C.c_float)
+                elif a.startswith("double"):
+                    types.append(C.c_double)
+                else:
+                    types.append(C.c_int)
+        fn = getattr(lib, name)
+        fn.argtypes = types
+        fn.restype = C.c_int
 
 
 def lib() -> C.CDLL:
@@ -71,6 +103,7 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
                 f"Build it with `bash {BUILD_SCRIPT}` or `python -c 'import __graft_entry__ as g; g.build()'`.")
         _lib = C.CDLL(LIB_PATH)
+        _declare_prototypes(_lib)
         _lib.pn_last_error.restype = C.c_char_p
         _lib.pn_version.restype = C.c_int
         _lib.pn_launch_count.restype = C.c_longlong

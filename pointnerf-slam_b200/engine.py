@@ -266,7 +266,7 @@ def plan_forward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, dev
     apply_mask = 1 if mb is not None else 0
     with torch.cuda.device(device):
         for i, p in enumerate(plan.passes):
-            stash = Stash(p, n, device, bool(want_w[i])) if save else None
+            stash = Stash(p, n, device, bool(want_w[i])) if (save and p.kind != "imap") else None
             stashes.append(stash)
             sst = stash.struct() if stash is not None else None
             nb = host_bound(p.norm_bound)

@@ -1,0 +1,79 @@
+"""Host glue for the iMAP* single-MLP decoder kernels (pn_imap_mlp_fwd / _bwd)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+
+
+class PnImapMlpGrad(C.Structure):
+    _fields_ = [("B", L.P), ("W", L.P * 8), ("b", L.P * 8), ("Wo", L.P), ("bo", L.P)]
+
+
+def _struct(p) -> L.PnImapMlp:
+    t = p.params  # [B, W0.., b0.., Wo, bo]
+    nb = (len(t) - 3) // 2
+    if nb > 8:
+        raise RuntimeError("iMAP decoder: at most 8 blocks are supported")
+    m = L.PnImapMlp()
+    m.B = t[0].data_ptr()
+    for i in range(nb):
+        m.W[i] = t[1 + i].data_ptr()
+        m.b[i] = t[1 + nb + i].data_ptr()
+    m.Wo, m.bo = t[1 + 2 * nb].data_ptr(), t[2 + 2 * nb].data_ptr()
+    m.hidden, m.n_blocks = t[1].shape[0], nb
+    if t[1].shape[1] != 93 or t[1 + 2 * nb].shape[0] != 4 or any(s in getattr(p.dec, "skips", []) for s in range(nb)):
+        raise RuntimeError("iMAP decoder must be Fourier-93 -> hidden x n_blocks (no skips) -> 4")
+    return m
+
+
+class ImapStash:
+    def __init__(self, n: int, hidden: int, n_blocks: int, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.E = torch.empty(n * 96, **f32)
+        self.H = torch.empty(n_blocks * n * hidden, **f32)
+        self.P32 = torch.empty(3 * n, **f32)
+
+
+def forward(p, pts, raw: torch.Tensor, mask_bound, device, save: bool, want_w: bool) -> Optional[ImapStash]:
+    m = _struct(p)
+    n = pts.n
+    st = ImapStash(n, m.hidden, m.n_blocks, device)
+    ps = pts.struct()
+    mb = L.f64x6(mask_bound) if mask_bound is not None else None
+    with L.timed("imap_mlp_fwd", device):
+        L.check(L.lib().pn_imap_mlp_fwd(C.byref(ps), C.byref(m), mb, 1 if mb is not None else 0, C.c_void_p(raw.data_ptr()),
+                                        C.c_void_p(st.E.data_ptr()), C.c_void_p(st.H.data_ptr()), C.c_void_p(st.P32.data_ptr()),
+                                        C.c_void_p(L.stream_ptr(device))), "pn_imap_mlp_fwd")
+    return st if save else None
+
+
+def backward(p, pts, g_raw: torch.Tensor, stash: ImapStash, g_pts: Optional[torch.Tensor], mask_bound, device,
+             want_w: bool) -> Optional[List[torch.Tensor]]:
+    m = _struct(p)
+    n = pts.n
+    f32 = dict(dtype=torch.float32, device=device)
+    width = max(m.hidden, 96)
+    GA, GB, GO = torch.empty(n * width, **f32), torch.empty(n * width, **f32), torch.empty(n * 4, **f32)
+    gp = g = None
+    if want_w:
+        gp = [torch.zeros_like(t) for t in p.params]
+        nb = m.n_blocks
+        g = PnImapMlpGrad()
+        g.B = gp[0].data_ptr()
+        for i in range(nb):
+            g.W[i] = gp[1 + i].data_ptr()
+            g.b[i] = gp[1 + nb + i].data_ptr()
+        g.Wo, g.bo = gp[1 + 2 * nb].data_ptr(), gp[2 + 2 * nb].data_ptr()
+    ps = pts.struct()
+    mb = L.f64x6(mask_bound) if mask_bound is not None else None
+    with L.timed("imap_mlp_bwd", device):
+        L.check(L.lib().pn_imap_mlp_bwd(C.byref(ps), C.byref(m), mb, 1 if mb is not None else 0, C.c_void_p(g_raw.data_ptr()),
+                                        C.c_void_p(stash.E.data_ptr()), C.c_void_p(stash.H.data_ptr()),
+                                        C.c_void_p(stash.P32.data_ptr()), C.c_void_p(GA.data_ptr()), C.c_void_p(GB.data_ptr()),
+                                        C.c_void_p(GO.data_ptr()), C.c_void_p(L.ptr(g_pts)), C.byref(g) if g is not None else None,
+                                        C.c_void_p(L.stream_ptr(device))), "pn_imap_mlp_bwd")
+    return gp

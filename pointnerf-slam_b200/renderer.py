@@ -286,7 +286,7 @@ class Renderer(object):
         with torch.cuda.device(dev):
             L.check(L.lib().pn_regulation_points(C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(gt.data_ptr()),
                                                  C.c_void_p(k["t_vals"].data_ptr()), C.c_void_p(t_rand.data_ptr()),
-                                                 C.c_int64(R), self.N_samples, C.c_void_p(pts.data_ptr()),
+                                                 C.c_int64(R), self.N_samples, C.c_void_p(pts.data_ptr()), None,
                                                  C.c_void_p(L.stream_ptr(dev))), "pn_regulation_points")
         raw = self.eval_points(pts, decoders, c, stage, device)
         return raw[:, -1]

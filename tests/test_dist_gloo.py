@@ -1,0 +1,71 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2): ray sharding, the shared
+batch depth maximum and the SUM all-reduce of gradients reproduce the
+un-sharded oracle gradients."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from pointnerf_slam_b200 import dist as D
+    from oracle import nice_oracle as O
+    from tests import helpers as T
+    r, w, _ = D.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.set_num_threads(1)
+    g = T.load_nice()
+    n = g["rays_o"].shape[0]
+    b, e = D.shard_bounds(n, rank, world)
+    grids = {k: g[k].clone().requires_grad_(True) for k in O.GRID_KEYS}
+    sd = {k: v.clone().requires_grad_(k.startswith("color_decoder.")) for k, v in T.state_dict(g).items()}
+    gd = g["gt_depth"][b:e]
+    dmax = D.share_depth_max(gd)
+    assert float(dmax) == float(g["gt_depth"].max())
+    # the oracle takes the batch maximum from the tensor it is given: append a far, zero-weight
+    # sentinel so that every shard sees the global maximum (what depth_max_override does on GPU)
+    scene = T.oracle_scene(g, grids, sd)
+    ro, rd, gc = g["rays_o"][b:e], g["rays_d"][b:e], g["gt_color"][b:e]
+    ro2 = torch.cat([ro, ro[:1]]); rd2 = torch.cat([rd, rd[:1]]); gd2 = torch.cat([gd, dmax])
+    d, v, c = O.render_batch_ray(scene, rd2, ro2, "color", gd2)
+    loss = O.mapping_loss(d[:-1], c[:-1], gd, gc, "color")
+    loss.backward()
+    trained = [grids[k] for k in ("grid_middle", "grid_fine", "grid_color")] + [p for p in sd.values() if p.requires_grad]
+    D.allreduce_gradients([t.grad for t in trained])
+    if rank == 0:
+        torch.save({"grads": [t.grad for t in trained]}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_mapping_matches_full(tmp_path):
+    from oracle import nice_oracle as O
+    from tests import helpers as T
+    out = str(tmp_path / "g.pt")
+    port = 29000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)["grads"]
+    g = T.load_nice()
+    keys = ["color/map/grad_grid_middle", "color/map/grad_grid_fine", "color/map/grad_grid_color"]
+    for a, k in zip(got[:3], keys):
+        assert T.rel_max(a, g[k]) < 1e-4, k
+    names = [k for k in T.state_dict(g) if k.startswith("color_decoder.")]
+    for a, nme in zip(got[3:], names):
+        assert T.rel_max(a, g["color/map/gradsd/" + nme]) < 1e-4, nme
+
+
+def test_shard_bounds_cover_everything():
+    from pointnerf_slam_b200 import dist as D
+    for n in (0, 1, 7, 96, 5000):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
