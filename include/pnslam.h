@@ -250,6 +250,10 @@ int pn_composite_bwd(const float* raw, const double* z, const float* rays_d, int
 int pn_points_to_rays_bwd(const float* g_pts, const double* z, int64_t R, int S,
                           float* g_rays_o, float* g_rays_d, void* stream);
 
+/* tcgen05 self-test: Y (128,32) = X (128,K) . W (32,K)^T through the 3xTF32 tensor-core path
+ * (operands in shared memory, accumulator in tensor memory); K multiple of 8, <= 128. */
+int pn_tc_selftest(const float* X, const float* W, float* Y, int K, void* stream);
+
 /* -------- utilities -------- */
 /* (1,32,Z,Y,X) contiguous <-> channels-last [Z][Y][X][32]; `to_channels_last` = 1 or 0. */
 int pn_grid_transpose(const float* src, float* dst, int D, int H, int W, int to_channels_last, void* stream);
