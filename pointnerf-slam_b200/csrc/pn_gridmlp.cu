@@ -18,7 +18,10 @@
 //   * MLP phase, thread = sample: activations live in registers, weights are
 //     staged once per CTA in shared memory ([out][in] rows, 16-byte aligned)
 //     and read as warp-uniform LDS.128 broadcasts.
+#include <stdlib.h>
+
 #include "pn_common.cuh"
+#include "pn_umma.cuh"
 
 namespace pn {
 namespace {
@@ -580,8 +583,271 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_B(const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// forward on the 5th-gen tensor cores (tcgen05, kind::tf32, 3xTF32 split)
+// ---------------------------------------------------------------------------
+// CTA = 256 threads = two independent groups of 128; a group owns one tile of 128 consecutive
+// samples at a time (thread = sample row = TMEM lane).  Per tile every decoder layer is a
+// D[128 x 32] (+)= A[128 x K] . W[32 x K]^T tensor-core product: the activation operand A is
+// written by the group (hi and lo copies, canonical K-major layout) into its 32 KB shared
+// buffer, the weights sit pre-split in shared memory for the whole kernel, the accumulators
+// live in the group's 256 tensor-memory columns:
+//     cols   0..159  D2_l = Wc_l . c           (feature term of block l, issued up front)
+//     cols 160..191  D1_0 = W0 . emb           (3 K-chunks of 32)
+//     cols 192..223  D1_3 = W3[:, :93] . emb + W3[:, 93:] . h2
+//     cols 224..255  D1_x = W_l . h_{l-1}      (blocks 1, 2, 4)
+// The epilogue of a block reads its accumulators back (tcgen05.ld), applies
+// relu(D1 + b) + D2 + bc in registers, records the ReLU bits / stash, re-splits into hi/lo
+// and stores the next A operand.  While one group waits for its MMAs the other group runs.
+namespace tc {
+constexpr uint32_t kLbo = 128;                       // core matrices adjacent in K
+constexpr uint32_t kASbo = 8 * 128;                  // A buffer: K = 32 per 8-row group
+constexpr uint32_t kABytes = 16 * kASbo;             // one 128 x 32 operand copy (16 KB)
+__host__ __device__ constexpr uint32_t bsbo(int K) { return (uint32_t)(K / 4) * 128u; }
+__host__ __device__ constexpr uint32_t bbytes(int K) { return 4u * bsbo(K); }  // 32 rows
+// byte offsets of the pre-split weight operands (hi copy; lo copy follows at +bbytes)
+constexpr uint32_t O_W0 = 0;
+constexpr uint32_t O_W3E = O_W0 + 2 * bbytes(96);
+constexpr uint32_t O_WH = O_W3E + 2 * bbytes(96);    // 4 x [32 x 32]
+constexpr uint32_t O_WC = O_WH + 4 * 2 * bbytes(32);
+template <int CD> __host__ __device__ constexpr uint32_t o_a() { return O_WC + 5u * 2u * bbytes(CD); }   // A buffers
+template <int CD> __host__ __device__ constexpr uint32_t o_small() { return o_a<CD>() + 2u * 2u * kABytes; }
+constexpr int S_B = 0, S_BIAS = 288, S_BC = 448, S_WO = 608, S_BO = 736, S_TOTAL = 740;  // floats
+// the two mbarriers and the TMEM base address follow the float area (kept in dynamic shared
+// memory: with c_dim 64 the kernel uses all but ~100 bytes of the 227 KB an SM offers)
+template <int CD> __host__ __device__ constexpr uint32_t smem_total() { return o_small<CD>() + S_TOTAL * 4u + 24u; }
+
+// split a [32 x K] row-major weight block (row stride ld, starting column col0, `kvalid` real
+// columns, zero beyond) into canonical hi / lo operands
+__device__ __forceinline__ void stage_b(unsigned char* hi, const float* __restrict__ src, int ld, int col0, int K, int kvalid) {
+  unsigned char* lo = hi + bbytes(K);
+  for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    const float w = k < kvalid ? src[n * ld + col0 + k] : 0.f;
+    float h, l;
+    umma::split_tf32(w, h, l);
+    const uint32_t off = umma::kmajor_off(n, k, kLbo, bsbo(K));
+    *reinterpret_cast<float*>(hi + off) = h;
+    *reinterpret_cast<float*>(lo + off) = l;
+  }
+}
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+// write this thread's 32-wide row (hi and lo) into the group's A buffer
+__device__ __forceinline__ void store_row(unsigned char* a_hi, int row, const float (&v)[32]) {
+  unsigned char* a_lo = a_hi + kABytes;
+  const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 h, l;
+    umma::split_tf32(v[4 * q], h.x, l.x); umma::split_tf32(v[4 * q + 1], h.y, l.y);
+    umma::split_tf32(v[4 * q + 2], h.z, l.z); umma::split_tf32(v[4 * q + 3], h.w, l.w);
+    *reinterpret_cast<float4*>(a_hi + base + q * kLbo) = h;
+    *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
+  }
+}
+
+// Trilinear features of the group's 128 rows straight into the A operand.  8 lanes per
+// sample (lane&7 = channel quad, 128-bit loads), 4 samples per warp iteration.
+__device__ __forceinline__ void gather_rows(const GridDev& g, float ux, float uy, float uz, unsigned valid_mask, int lane,
+                                            int warp_row0, unsigned char* a_hi, float* __restrict__ Cst, int64_t N, int64_t n0) {
+  unsigned char* a_lo = a_hi + kABytes;
+  const int q = lane & 7, sub = lane >> 3;
+#pragma unroll 2
+  for (int it = 0; it < 8; ++it) {
+    const int src = 4 * it + sub;
+    const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((valid_mask >> src) & 1u) {
+      const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
+      const float4* gp = reinterpret_cast<const float4*>(g.data + c.base) + q;
+      float4 val[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        val[k] = ((c.ok >> k) & 1u) ? __ldg(gp + corner_offset(k, g.W, g.H) / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if ((c.ok >> k) & 1u) {
+          const float w = corner_weight(c, k);
+          v.x = __fadd_rn(v.x, __fmul_rn(val[k].x, w)); v.y = __fadd_rn(v.y, __fmul_rn(val[k].y, w));
+          v.z = __fadd_rn(v.z, __fmul_rn(val[k].z, w)); v.w = __fadd_rn(v.w, __fmul_rn(val[k].w, w));
+        }
+      }
+      if (Cst) reinterpret_cast<float4*>(Cst)[(int64_t)q * N + n0 + src] = v;
+    }
+    const int row = warp_row0 + src;
+    float4 h, l;
+    umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y); umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+    const uint32_t off = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)q * kLbo;
+    *reinterpret_cast<float4*>(a_hi + off) = h;
+    *reinterpret_cast<float4*>(a_lo + off) = l;
+  }
+}
+}  // namespace tc
+
+template <int CD, int NOUT>
+__global__ void __launch_bounds__(256, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  using namespace tc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid >> 7, row = tid & 127, gwarp = warp & 3;
+  float* sm = reinterpret_cast<float*>(smraw + o_small<CD>());
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S_TOTAL);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 4);
+  unsigned char* a_hi = smraw + o_a<CD>() + (uint32_t)grp * 2u * kABytes;
+  // ---- one-time set-up: TMEM, barriers, weights
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
+  stage_b(smraw + O_W0, a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
+  stage_b(smraw + O_W3E, a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
+  stage_b(smraw + O_WH, a.w.W[1], 32, 0, 32, 32);
+  stage_b(smraw + O_WH + 2 * bbytes(32), a.w.W[2], 32, 0, 32, 32);
+  stage_b(smraw + O_WH + 4 * bbytes(32), a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
+  stage_b(smraw + O_WH + 6 * bbytes(32), a.w.W[4], 32, 0, 32, 32);
+  for (int l = 0; l < 5; ++l) stage_b(smraw + O_WC + (uint32_t)l * 2u * bbytes(CD), a.w.Wc[l], CD, 0, CD, CD);
+  for (int i = tid; i < 288; i += 256) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
+  for (int i = tid; i < 160; i += 256) { sm[S_BIAS + i] = a.w.b[i >> 5][i & 31]; sm[S_BC + i] = a.w.bc[i >> 5][i & 31]; }
+  for (int i = tid; i < 128; i += 256) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
+  if (tid < 4) sm[S_BO + tid] = tid < NOUT ? a.w.bo[tid] : 0.f;
+  umma::fence_proxy_async();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = tmem_base_s + (uint32_t)grp * 256u;           // this group's columns
+  const uint32_t tm_lane = tm + ((uint32_t)(gwarp * 32) << 16);      // this warp's lanes
+  const uint32_t sA = umma::smem_u32(a_hi), sAlo = sA + kABytes;
+  const uint32_t sW = umma::smem_u32(smraw);
+  constexpr uint32_t idesc = umma::instr_desc_tf32(128, 32);
+  uint64_t* bar = &bars[grp];
+  uint32_t phase = 0;
+  const bool issuer = row == 0;
+  // D(+)= A . B[:, 32*k32 .. 32*k32+31] of the [32 x Kb] operand at byte offset boff
+  auto mma = [&](uint32_t dcol, uint32_t boff, int Kb, int k32, uint32_t acc) {
+    const uint32_t bh = sW + boff + (uint32_t)k32 * 8u * kLbo;
+    umma::mma_3xtf32(tm + dcol, sA, sAlo, kLbo, kASbo, bh, bh + bbytes(Kb), kLbo, bsbo(Kb), 32, idesc, acc);
+  };
+  auto publish_and_issue = [&](auto&& issue) {   // A written -> MMAs -> wait for completion
+    umma::fence_proxy_async();
+    umma::tc_fence_before();
+    group_sync(grp);
+    if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::tc_fence_after();
+  };
+
+  const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
+  for (int64_t t = (int64_t)blockIdx.x * 2 + grp; t < ntiles; t += (int64_t)gridDim.x * 2) {
+    const int64_t n = t * 128 + row;
+    const bool valid = n < N;
+    Sample sp;
+    sp.pf[0] = sp.pf[1] = sp.pf[2] = 0.f; sp.xn[0] = sp.xn[1] = sp.xn[2] = 0.f; sp.inside = true;
+    if (valid) load_sample(a.pts, n, a.nb, a.mb, sp);
+    const unsigned vm = __ballot_sync(kFull, valid);
+    // ---- feature terms of all five blocks
+    gather_rows(a.ga, unnormalise(sp.xn[0], a.ga.W), unnormalise(sp.xn[1], a.ga.H), unnormalise(sp.xn[2], a.ga.D), vm, lane,
+                gwarp * 32, a_hi, a.C, N, t * 128 + gwarp * 32);
+    publish_and_issue([&] {
+      for (int l = 0; l < 5; ++l) mma(32u * l, O_WC + (uint32_t)l * 2u * bbytes(CD), CD, 0, 0u);
+    });
+    if (CD == 64) {
+      gather_rows(a.gb, unnormalise(sp.xn[0], a.gb.W), unnormalise(sp.xn[1], a.gb.H), unnormalise(sp.xn[2], a.gb.D), vm, lane,
+                  gwarp * 32, a_hi, a.C ? a.C + (int64_t)32 * N : nullptr, N, t * 128 + gwarp * 32);
+      publish_and_issue([&] {
+        for (int l = 0; l < 5; ++l) mma(32u * l, O_WC + (uint32_t)l * 2u * bbytes(CD), CD, 1, 1u);
+      });
+    }
+    // ---- Fourier embedding, three K-chunks of 32
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      float e[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int kk = 32 * c + k;
+        e[k] = sinf(fmaf(sp.pf[2], sm[S_B + 192 + kk], fmaf(sp.pf[1], sm[S_B + 96 + kk], sp.pf[0] * sm[S_B + kk])));
+      }
+      if (a.E && valid) {
+        float4* o = reinterpret_cast<float4*>(a.E);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[(int64_t)(8 * c + q) * N + n] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+      }
+      store_row(a_hi, row, e);
+      publish_and_issue([&] { mma(160u, O_W0, 96, c, c > 0 ? 1u : 0u); mma(192u, O_W3E, 96, c, c > 0 ? 1u : 0u); });
+    }
+    // ---- blocks 0..4
+    float h[32];
+#pragma unroll 1
+    for (int l = 0; l < 5; ++l) {
+      float d1[32], d2[32];
+      const uint32_t c1 = (l == 0) ? 160u : (l == 3 ? 192u : 224u);
+      umma::tmem_ld32(tm_lane + c1, d1);
+      umma::tmem_ld32(tm_lane + 32u * l, d2);
+      uint32_t bits = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pre = d1[j] + sm[S_BIAS + l * 32 + j];
+        bits |= (pre > 0.f) ? (1u << j) : 0u;
+        h[j] = fmaxf(pre, 0.f) + (d2[j] + sm[S_BC + l * 32 + j]);
+      }
+      if (valid) {
+        if (a.relu_bits) a.relu_bits[(int64_t)l * N + n] = bits;
+        if (a.H) store_planar32(a.H + (int64_t)l * 32 * N, N, n, h);
+      }
+      if (l < 4) {
+        store_row(a_hi, row, h);
+        publish_and_issue([&] {
+          if (l == 2) mma(192u, O_WH + 4 * bbytes(32), 32, 0, 1u);          // D1_3 += W3[:, 93:] . h2
+          else mma(224u, O_WH + (uint32_t)(l == 3 ? 6 : 2 * l) * bbytes(32), 32, 0, 0u);  // W1, W2, W4
+        });
+      }
+    }
+    // ---- output layer (32 x NOUT, registers)
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+      float s = sm[S_BO + o];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s = fmaf(sm[S_WO + o * 32 + j], h[j], s);
+      out[o] = s;
+    }
+    if (valid) {
+      float4* r = reinterpret_cast<float4*>(a.raw) + n;
+      const bool force = a.apply_mask && !sp.inside;
+      if (NOUT == 4) {
+        *r = make_float4(out[0], out[1], out[2], force ? 100.f : out[3]);
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.out_mode != PN_OUT_SET_ALL) v = *r;
+        v.w = (a.out_mode == PN_OUT_ADD_W) ? v.w + out[0] : out[0];
+        if (force) v.w = 100.f;
+        *r = v;
+      }
+    }
+    // all of this tile's TMEM reads are complete (tcgen05.wait::ld) before the next tile's MMAs overwrite them
+    umma::tc_fence_before();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base_s, 512);
+}
+
+inline bool use_tensor_cores() {
+  const char* e = getenv("PN_MLP_ENGINE");   // "ffma" forces the exact-FP32 FFMA kernels
+  return !(e && e[0] == 'f');
+}
+
 template <int CD, int NOUT>
 int launch_fwd(const FwdArgs& a, cudaStream_t st) {
+  if (use_tensor_cores()) {
+    auto kern = k_grid_mlp_fwd_tc<CD, NOUT>;
+    const size_t sm = tc::smem_total<CD>();
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    const int64_t pairs = ((a.pts.N + 127) / 128 + 1) / 2;
+    const int grid = (int)((pairs < (int64_t)sm_count()) ? pairs : (int64_t)sm_count());
+    kern<<<grid, 256, sm, st>>>(a);
+    return launch_status("k_grid_mlp_fwd_tc");
+  }
   auto kern = k_grid_mlp_fwd<CD, NOUT>;
   const size_t sm = smem_bytes<CD>();
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
