@@ -266,10 +266,10 @@ __global__ void __launch_bounds__(kThreads, CD == 32 ? 2 : 1) k_grid_mlp_fwd(con
       const float4 b0 = ld4(wsm + OFF_B + 4 * kc), b1 = ld4(wsm + OFF_B + kEP + 4 * kc),
                    b2 = ld4(wsm + OFF_B + 2 * kEP + 4 * kc);
       float e[4];
-      e[0] = sinf(fmaf(sp.pf[2], b2.x, fmaf(sp.pf[1], b1.x, sp.pf[0] * b0.x)));
-      e[1] = sinf(fmaf(sp.pf[2], b2.y, fmaf(sp.pf[1], b1.y, sp.pf[0] * b0.y)));
-      e[2] = sinf(fmaf(sp.pf[2], b2.z, fmaf(sp.pf[1], b1.z, sp.pf[0] * b0.z)));
-      e[3] = sinf(fmaf(sp.pf[2], b2.w, fmaf(sp.pf[1], b1.w, sp.pf[0] * b0.w)));
+      e[0] = fourier_sin(fmaf(sp.pf[2], b2.x, fmaf(sp.pf[1], b1.x, sp.pf[0] * b0.x)));
+      e[1] = fourier_sin(fmaf(sp.pf[2], b2.y, fmaf(sp.pf[1], b1.y, sp.pf[0] * b0.y)));
+      e[2] = fourier_sin(fmaf(sp.pf[2], b2.z, fmaf(sp.pf[1], b1.z, sp.pf[0] * b0.z)));
+      e[3] = fourier_sin(fmaf(sp.pf[2], b2.w, fmaf(sp.pf[1], b1.w, sp.pf[0] * b0.w)));
       if (a.E && valid) reinterpret_cast<float4*>(a.E)[(int64_t)kc * N + n] = make_float4(e[0], e[1], e[2], e[3]);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_grid_mlp_bwd(const BwdArgs a) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float arg = fmaf(sp.pf[2], bz[q], fmaf(sp.pf[1], by[q], sp.pf[0] * bx[q]));
-          gq[q] = ge[q] * cosf(arg);
+          gq[q] = ge[q] * fourier_cos(arg);
           gp[0] = fmaf(bx[q], gq[q], gp[0]); gp[1] = fmaf(by[q], gq[q], gp[1]); gp[2] = fmaf(bz[q], gq[q], gp[2]);
         }
         if (WS && valid) reinterpret_cast<float4*>(a.GARG)[(int64_t)kc * N + n] = make_float4(gq[0], gq[1], gq[2], gq[3]);
@@ -654,7 +654,7 @@ __device__ __forceinline__ void gather_rows(const GridDev& g, float ux, float uy
                                             int warp_row0, unsigned char* a_hi, float* __restrict__ Cst, int64_t N, int64_t n0) {
   unsigned char* a_lo = a_hi + kABytes;
   const int q = lane & 7, sub = lane >> 3;
-#pragma unroll 2
+#pragma unroll 4
   for (int it = 0; it < 8; ++it) {
     const int src = 4 * it + sub;
     const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
@@ -686,18 +686,38 @@ __device__ __forceinline__ void gather_rows(const GridDev& g, float ux, float uy
 }
 }  // namespace tc
 
+// TMEM -> registers, 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// CTA = 512 threads = two groups of 256.  Inside a group TWO threads serve each of the 128
+// sample rows: warp (quarter q = warp&3, half = warp>>2) owns rows 32q..32q+31 (the TMEM lanes
+// a warp with that id may address) and columns [16*half, 16*half+16) of every 32-wide operand.
 template <int CD, int NOUT>
-__global__ void __launch_bounds__(256, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
+__global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using namespace tc;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = tid >> 7, row = tid & 127, gwarp = warp & 3;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid >> 8, gw = (tid >> 5) & 7, quarter = gw & 3, half = gw >> 2;
+  const int row = quarter * 32 + lane, col0 = 16 * half;
   float* sm = reinterpret_cast<float*>(smraw + o_small<CD>());
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S_TOTAL);
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 4);
   unsigned char* a_hi = smraw + o_a<CD>() + (uint32_t)grp * 2u * kABytes;
+  unsigned char* a_lo = a_hi + kABytes;
   // ---- one-time set-up: TMEM, barriers, weights
-  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
+  if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
   stage_b(smraw + O_W0, a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
   stage_b(smraw + O_W3E, a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
@@ -706,35 +726,83 @@ __global__ void __launch_bounds__(256, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   stage_b(smraw + O_WH + 4 * bbytes(32), a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
   stage_b(smraw + O_WH + 6 * bbytes(32), a.w.W[4], 32, 0, 32, 32);
   for (int l = 0; l < 5; ++l) stage_b(smraw + O_WC + (uint32_t)l * 2u * bbytes(CD), a.w.Wc[l], CD, 0, CD, CD);
-  for (int i = tid; i < 288; i += 256) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
-  for (int i = tid; i < 160; i += 256) { sm[S_BIAS + i] = a.w.b[i >> 5][i & 31]; sm[S_BC + i] = a.w.bc[i >> 5][i & 31]; }
-  for (int i = tid; i < 128; i += 256) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
+  for (int i = tid; i < 288; i += 512) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
+  for (int i = tid; i < 160; i += 512) { sm[S_BIAS + i] = a.w.b[i >> 5][i & 31]; sm[S_BC + i] = a.w.bc[i >> 5][i & 31]; }
+  for (int i = tid; i < 128; i += 512) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
   if (tid < 4) sm[S_BO + tid] = tid < NOUT ? a.w.bo[tid] : 0.f;
   umma::fence_proxy_async();
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
-  const uint32_t tm = tmem_base_s + (uint32_t)grp * 256u;           // this group's columns
-  const uint32_t tm_lane = tm + ((uint32_t)(gwarp * 32) << 16);      // this warp's lanes
+  const uint32_t tm = tmem_base_s + (uint32_t)grp * 256u;               // this group's columns
+  const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);        // this warp's lanes
   const uint32_t sA = umma::smem_u32(a_hi), sAlo = sA + kABytes;
   const uint32_t sW = umma::smem_u32(smraw);
   constexpr uint32_t idesc = umma::instr_desc_tf32(128, 32);
   uint64_t* bar = &bars[grp];
   uint32_t phase = 0;
-  const bool issuer = row == 0;
+  const bool issuer = (tid & 255) == 0;
+  const uint64_t dA_hi = umma::smem_desc(sA, kLbo, kASbo), dA_lo = umma::smem_desc(sAlo, kLbo, kASbo);
+  constexpr uint32_t kStep = (2u * kLbo) >> 4;   // one K-step of 8 in descriptor address units
   // D(+)= A . B[:, 32*k32 .. 32*k32+31] of the [32 x Kb] operand at byte offset boff
   auto mma = [&](uint32_t dcol, uint32_t boff, int Kb, int k32, uint32_t acc) {
     const uint32_t bh = sW + boff + (uint32_t)k32 * 8u * kLbo;
-    umma::mma_3xtf32(tm + dcol, sA, sAlo, kLbo, kASbo, bh, bh + bbytes(Kb), kLbo, bsbo(Kb), 32, idesc, acc);
+    const uint64_t dB_hi = umma::smem_desc(bh, kLbo, bsbo(Kb)), dB_lo = umma::smem_desc(bh + bbytes(Kb), kLbo, bsbo(Kb));
+    umma::mma_3xtf32_k32(tm + dcol, dA_hi, dA_lo, dB_hi, dB_lo, kStep, kStep, idesc, acc);
   };
   auto publish_and_issue = [&](auto&& issue) {   // A written -> MMAs -> wait for completion
     umma::fence_proxy_async();
     umma::tc_fence_before();
-    group_sync(grp);
+    asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
     if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
     umma::mbar_wait(bar, phase);
     phase ^= 1u;
     umma::tc_fence_after();
+  };
+  // this thread's 16 columns of its row -> A operand (hi and lo)
+  auto store_half_row = [&](const float (&v)[16]) {
+    const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)(4 * half) * kLbo;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 h, l;
+      umma::split_tf32(v[4 * q], h.x, l.x); umma::split_tf32(v[4 * q + 1], h.y, l.y);
+      umma::split_tf32(v[4 * q + 2], h.z, l.z); umma::split_tf32(v[4 * q + 3], h.w, l.w);
+      *reinterpret_cast<float4*>(a_hi + base + q * kLbo) = h;
+      *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
+    }
+  };
+  // trilinear features of rows 32*quarter + 16*half + [0,16) -> A operand; 8 lanes per sample
+  auto gather16 = [&](const GridDev& g, float ux, float uy, float uz, unsigned vm, float* __restrict__ Cst, int64_t N, int64_t nq) {
+    const int q = lane & 7, sub = lane >> 3;
+#pragma unroll 2
+    for (int it = 0; it < 4; ++it) {
+      const int src = 16 * half + 4 * it + sub;   // lane (within this warp) that owns the row
+      const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((vm >> src) & 1u) {
+        const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
+        const float4* gp = reinterpret_cast<const float4*>(g.data + c.base) + q;
+        float4 val[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          val[k] = ((c.ok >> k) & 1u) ? __ldg(gp + corner_offset(k, g.W, g.H) / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if ((c.ok >> k) & 1u) {
+            const float w = corner_weight(c, k);
+            v.x = __fadd_rn(v.x, __fmul_rn(val[k].x, w)); v.y = __fadd_rn(v.y, __fmul_rn(val[k].y, w));
+            v.z = __fadd_rn(v.z, __fmul_rn(val[k].z, w)); v.w = __fadd_rn(v.w, __fmul_rn(val[k].w, w));
+          }
+        }
+        if (Cst) reinterpret_cast<float4*>(Cst)[(int64_t)q * N + nq + src] = v;
+      }
+      const int r = quarter * 32 + src;
+      float4 h, l;
+      umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y); umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+      const uint32_t off = (uint32_t)(r >> 3) * kASbo + (uint32_t)(r & 7) * 16u + (uint32_t)q * kLbo;
+      *reinterpret_cast<float4*>(a_hi + off) = h;
+      *reinterpret_cast<float4*>(a_lo + off) = l;
+    }
   };
 
   const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
@@ -745,91 +813,108 @@ __global__ void __launch_bounds__(256, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
     sp.pf[0] = sp.pf[1] = sp.pf[2] = 0.f; sp.xn[0] = sp.xn[1] = sp.xn[2] = 0.f; sp.inside = true;
     if (valid) load_sample(a.pts, n, a.nb, a.mb, sp);
     const unsigned vm = __ballot_sync(kFull, valid);
+    const int64_t nq = t * 128 + quarter * 32;
     // ---- feature terms of all five blocks
-    gather_rows(a.ga, unnormalise(sp.xn[0], a.ga.W), unnormalise(sp.xn[1], a.ga.H), unnormalise(sp.xn[2], a.ga.D), vm, lane,
-                gwarp * 32, a_hi, a.C, N, t * 128 + gwarp * 32);
+    gather16(a.ga, unnormalise(sp.xn[0], a.ga.W), unnormalise(sp.xn[1], a.ga.H), unnormalise(sp.xn[2], a.ga.D), vm, a.C, N, nq);
     publish_and_issue([&] {
       for (int l = 0; l < 5; ++l) mma(32u * l, O_WC + (uint32_t)l * 2u * bbytes(CD), CD, 0, 0u);
     });
     if (CD == 64) {
-      gather_rows(a.gb, unnormalise(sp.xn[0], a.gb.W), unnormalise(sp.xn[1], a.gb.H), unnormalise(sp.xn[2], a.gb.D), vm, lane,
-                  gwarp * 32, a_hi, a.C ? a.C + (int64_t)32 * N : nullptr, N, t * 128 + gwarp * 32);
+      gather16(a.gb, unnormalise(sp.xn[0], a.gb.W), unnormalise(sp.xn[1], a.gb.H), unnormalise(sp.xn[2], a.gb.D), vm,
+               a.C ? a.C + (int64_t)32 * N : nullptr, N, nq);
       publish_and_issue([&] {
         for (int l = 0; l < 5; ++l) mma(32u * l, O_WC + (uint32_t)l * 2u * bbytes(CD), CD, 1, 1u);
       });
     }
-    // ---- Fourier embedding, three K-chunks of 32
+    // ---- Fourier embedding, three K-chunks of 32 (16 columns per thread)
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
-      float e[32];
+      float e[16];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int kk = 32 * c + k;
-        e[k] = sinf(fmaf(sp.pf[2], sm[S_B + 192 + kk], fmaf(sp.pf[1], sm[S_B + 96 + kk], sp.pf[0] * sm[S_B + kk])));
+      for (int k = 0; k < 16; ++k) {
+        const int kk = 32 * c + col0 + k;
+        e[k] = fourier_sin(fmaf(sp.pf[2], sm[S_B + 192 + kk], fmaf(sp.pf[1], sm[S_B + 96 + kk], sp.pf[0] * sm[S_B + kk])));
       }
       if (a.E && valid) {
         float4* o = reinterpret_cast<float4*>(a.E);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o[(int64_t)(8 * c + q) * N + n] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          o[(int64_t)(8 * c + 4 * half + q) * N + n] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
       }
-      store_row(a_hi, row, e);
+      store_half_row(e);
       publish_and_issue([&] { mma(160u, O_W0, 96, c, c > 0 ? 1u : 0u); mma(192u, O_W3E, 96, c, c > 0 ? 1u : 0u); });
     }
-    // ---- blocks 0..4
-    float h[32];
+    // ---- blocks 0..3: each thread finishes its 16 columns
 #pragma unroll 1
-    for (int l = 0; l < 5; ++l) {
-      float d1[32], d2[32];
+    for (int l = 0; l < 4; ++l) {
+      float d1[16], d2[16], h[16];
       const uint32_t c1 = (l == 0) ? 160u : (l == 3 ? 192u : 224u);
-      umma::tmem_ld32(tm_lane + c1, d1);
-      umma::tmem_ld32(tm_lane + 32u * l, d2);
+      tmem_ld16(tm_lane + c1 + col0, d1);
+      tmem_ld16(tm_lane + 32u * l + col0, d2);
+      uint32_t bits = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float pre = d1[j] + sm[S_BIAS + l * 32 + col0 + j];
+        bits |= (pre > 0.f) ? (1u << j) : 0u;
+        h[j] = fmaxf(pre, 0.f) + (d2[j] + sm[S_BC + l * 32 + col0 + j]);
+      }
+      if (valid) {
+        if (a.relu_bits) reinterpret_cast<uint16_t*>(a.relu_bits)[((int64_t)l * N + n) * 2 + half] = (uint16_t)bits;
+        if (a.H) {
+          float4* o = reinterpret_cast<float4*>(a.H + (int64_t)l * 32 * N);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[(int64_t)(4 * half + q) * N + n] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        }
+      }
+      store_half_row(h);
+      publish_and_issue([&] {
+        if (l == 2) mma(192u, O_WH + 4 * bbytes(32), 32, 0, 1u);          // D1_3 += W3[:, 93:] . h2
+        else mma(224u, O_WH + (uint32_t)(l == 3 ? 6 : 2 * l) * bbytes(32), 32, 0, 0u);  // W1, W2, W4
+      });
+    }
+    // ---- block 4 + output layer: half 0 finishes the whole row (32 columns)
+    if (half == 0) {
+      float d1[32], d2[32], h[32];
+      umma::tmem_ld32(tm_lane + 224u, d1);
+      umma::tmem_ld32(tm_lane + 128u, d2);
       uint32_t bits = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float pre = d1[j] + sm[S_BIAS + l * 32 + j];
+        const float pre = d1[j] + sm[S_BIAS + 128 + j];
         bits |= (pre > 0.f) ? (1u << j) : 0u;
-        h[j] = fmaxf(pre, 0.f) + (d2[j] + sm[S_BC + l * 32 + j]);
+        h[j] = fmaxf(pre, 0.f) + (d2[j] + sm[S_BC + 128 + j]);
+      }
+      float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) {
+        float s = sm[S_BO + o];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s = fmaf(sm[S_WO + o * 32 + j], h[j], s);
+        out[o] = s;
       }
       if (valid) {
-        if (a.relu_bits) a.relu_bits[(int64_t)l * N + n] = bits;
-        if (a.H) store_planar32(a.H + (int64_t)l * 32 * N, N, n, h);
-      }
-      if (l < 4) {
-        store_row(a_hi, row, h);
-        publish_and_issue([&] {
-          if (l == 2) mma(192u, O_WH + 4 * bbytes(32), 32, 0, 1u);          // D1_3 += W3[:, 93:] . h2
-          else mma(224u, O_WH + (uint32_t)(l == 3 ? 6 : 2 * l) * bbytes(32), 32, 0, 0u);  // W1, W2, W4
-        });
-      }
-    }
-    // ---- output layer (32 x NOUT, registers)
-    float out[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int o = 0; o < NOUT; ++o) {
-      float s = sm[S_BO + o];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) s = fmaf(sm[S_WO + o * 32 + j], h[j], s);
-      out[o] = s;
-    }
-    if (valid) {
-      float4* r = reinterpret_cast<float4*>(a.raw) + n;
-      const bool force = a.apply_mask && !sp.inside;
-      if (NOUT == 4) {
-        *r = make_float4(out[0], out[1], out[2], force ? 100.f : out[3]);
-      } else {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.out_mode != PN_OUT_SET_ALL) v = *r;
-        v.w = (a.out_mode == PN_OUT_ADD_W) ? v.w + out[0] : out[0];
-        if (force) v.w = 100.f;
-        *r = v;
+        if (a.relu_bits) a.relu_bits[(int64_t)4 * N + n] = bits;
+        if (a.H) store_planar32(a.H + (int64_t)4 * 32 * N, N, n, h);
+        float4* r = reinterpret_cast<float4*>(a.raw) + n;
+        const bool force = a.apply_mask && !sp.inside;
+        if (NOUT == 4) {
+          *r = make_float4(out[0], out[1], out[2], force ? 100.f : out[3]);
+        } else {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.out_mode != PN_OUT_SET_ALL) v = *r;
+          v.w = (a.out_mode == PN_OUT_ADD_W) ? v.w + out[0] : out[0];
+          if (force) v.w = 100.f;
+          *r = v;
+        }
       }
     }
-    // all of this tile's TMEM reads are complete (tcgen05.wait::ld) before the next tile's MMAs overwrite them
+    // this tile's TMEM reads (tcgen05.wait::ld) are ordered before the next tile's MMAs by the
+    // fence + group barrier inside the next publish_and_issue
     umma::tc_fence_before();
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem_base_s, 512);
+  if (tid < 32) umma::tmem_dealloc(tmem_base_s, 512);
 }
 
 inline bool use_tensor_cores() {
@@ -845,7 +930,7 @@ int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     const int64_t pairs = ((a.pts.N + 127) / 128 + 1) / 2;
     const int grid = (int)((pairs < (int64_t)sm_count()) ? pairs : (int64_t)sm_count());
-    kern<<<grid, 256, sm, st>>>(a);
+    kern<<<grid, 512, sm, st>>>(a);
     return launch_status("k_grid_mlp_fwd_tc");
   }
   auto kern = k_grid_mlp_fwd<CD, NOUT>;
@@ -858,8 +943,284 @@ int launch_fwd(const FwdArgs& a, cudaStream_t st) {
   return launch_status("k_grid_mlp_fwd");
 }
 
+// ---------------------------------------------------------------------------
+// backward (input gradients) on the tensor cores
+// ---------------------------------------------------------------------------
+// Same tiling as the forward: CTA = 2 groups x 256 threads, two threads per sample row.
+// Every transposed mat-vec of the FFMA kernel becomes D[128 x N] (+)= G[128 x 32] . (W^T)[N x 32]^T
+// with the gradient operand G (hi/lo) in the group's shared buffer and the transposed weights
+// pre-split in shared memory.  Tensor-memory columns per group:
+//     0..31   D_gc = sum_l gh_l . Wc_l[:, :32]      (feature gradient, accumulated over blocks)
+//    32..63   D_x  = ga_l . W_l                     (gradient at the previous block's output)
+//    64..159  D_ge = ga_3 . W3[:, :93] + ga_0 . W0  (gradient at the Fourier embedding)
+namespace tcb {
+using tc::kLbo; using tc::kASbo; using tc::kABytes;
+constexpr uint32_t kBB = 4096;                 // one [32 x 32] operand copy
+constexpr uint32_t kBE = 12288;                // one [96 x 32] operand copy
+constexpr uint32_t O_WT = 0;                   // W1^T, W2^T, W3h^T, W4^T (hi, lo each)
+constexpr uint32_t O_WCT = O_WT + 8 * kBB;     // Wc_l[:, :32]^T, l = 0..4
+constexpr uint32_t O_W0T = O_WCT + 10 * kBB;   // W0^T  [96 x 32]
+constexpr uint32_t O_W3ET = O_W0T + 2 * kBE;   // W3[:, :93]^T
+constexpr uint32_t O_A = O_W3ET + 2 * kBE;     // 2 groups x (hi, lo)
+constexpr uint32_t O_SMALL = O_A + 4 * kABytes;
+constexpr int S_B = 0, S_WO = 288, S_TOTAL = 416;  // floats
+constexpr uint32_t kSmem = O_SMALL + S_TOTAL * 4u + 24u;
+constexpr int kTileLd = 33;                    // padded row of the feature-gradient tile (reuses the A buffer)
+
+// B operand = transpose of a row-major [32 x ld] weight block: element (n, j) = src[j*ld + col0 + n], n < nrows
+__device__ __forceinline__ void stage_bt(unsigned char* hi, uint32_t copy_bytes, const float* __restrict__ src, int ld, int col0,
+                                         int nrows, int nvalid) {
+  unsigned char* lo = hi + copy_bytes;
+  for (int i = threadIdx.x; i < nrows * 32; i += blockDim.x) {
+    const int j = i / nrows, n = i - j * nrows;   // n fastest: coalesced over the source row
+    const float w = n < nvalid ? src[j * ld + col0 + n] : 0.f;
+    float h, l;
+    umma::split_tf32(w, h, l);
+    const uint32_t off = umma::kmajor_off(n, j, kLbo, 1024u);
+    *reinterpret_cast<float*>(hi + off) = h;
+    *reinterpret_cast<float*>(lo + off) = l;
+  }
+}
+}  // namespace tcb
+
+template <int CD, int NOUT, bool GRID_GRAD, bool NEED_DP, bool WS>
+__global__ void __launch_bounds__(512, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  using namespace tcb;
+  constexpr bool EMB = NEED_DP || WS;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid >> 8, gw = (tid >> 5) & 7, quarter = gw & 3, half = gw >> 2;
+  const int row = quarter * 32 + lane, col0 = 16 * half;
+  float* sm = reinterpret_cast<float*>(smraw + O_SMALL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S_TOTAL);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 4);
+  unsigned char* a_hi = smraw + O_A + (uint32_t)grp * 2u * kABytes;
+  unsigned char* a_lo = a_hi + kABytes;
+  float* gtile = reinterpret_cast<float*>(a_hi);   // [128][33] floats, valid between the last MMA and the next tile
+  if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
+  stage_bt(smraw + O_WT, kBB, a.w.W[1], 32, 0, 32, 32);
+  stage_bt(smraw + O_WT + 2 * kBB, kBB, a.w.W[2], 32, 0, 32, 32);
+  stage_bt(smraw + O_WT + 4 * kBB, kBB, a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
+  stage_bt(smraw + O_WT + 6 * kBB, kBB, a.w.W[4], 32, 0, 32, 32);
+  for (int l = 0; l < 5; ++l) stage_bt(smraw + O_WCT + (uint32_t)l * 2u * kBB, kBB, a.w.Wc[l], CD, 0, 32, 32);
+  if (EMB) {
+    stage_bt(smraw + O_W0T, kBE, a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
+    stage_bt(smraw + O_W3ET, kBE, a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
+  }
+  for (int i = tid; i < 288; i += 512) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
+  for (int i = tid; i < 128; i += 512) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
+  umma::fence_proxy_async();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = tmem_base_s + (uint32_t)grp * 256u;
+  const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t sA = umma::smem_u32(a_hi), sW = umma::smem_u32(smraw);
+  constexpr uint32_t idesc32 = umma::instr_desc_tf32(128, 32), idesc96 = umma::instr_desc_tf32(128, 96);
+  uint64_t* bar = &bars[grp];
+  uint32_t phase = 0;
+  const bool issuer = (tid & 255) == 0;
+  const uint64_t dA_hi = umma::smem_desc(sA, kLbo, kASbo), dA_lo = umma::smem_desc(sA + kABytes, kLbo, kASbo);
+  constexpr uint32_t kStep = (2u * kLbo) >> 4;
+  auto mma = [&](uint32_t dcol, uint32_t boff, uint32_t copy_bytes, uint32_t idesc, uint32_t acc) {
+    const uint64_t dB_hi = umma::smem_desc(sW + boff, kLbo, 1024u), dB_lo = umma::smem_desc(sW + boff + copy_bytes, kLbo, 1024u);
+    umma::mma_3xtf32_k32(tm + dcol, dA_hi, dA_lo, dB_hi, dB_lo, kStep, kStep, idesc, acc);
+  };
+  auto group_bar = [&] { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); };
+  auto publish_issue = [&](auto&& issue) {
+    umma::fence_proxy_async();
+    umma::tc_fence_before();
+    group_bar();
+    if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
+  };
+  auto wait_mma = [&] { umma::mbar_wait(bar, phase); phase ^= 1u; umma::tc_fence_after(); };
+  auto store_half_row = [&](const float (&v)[16]) {
+    const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)(4 * half) * kLbo;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 h, l;
+      umma::split_tf32(v[4 * q], h.x, l.x); umma::split_tf32(v[4 * q + 1], h.y, l.y);
+      umma::split_tf32(v[4 * q + 2], h.z, l.z); umma::split_tf32(v[4 * q + 3], h.w, l.w);
+      *reinterpret_cast<float4*>(a_hi + base + q * kLbo) = h;
+      *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
+    }
+  };
+  auto stash_half = [&](float* base, int64_t N, int64_t n, const float (&v)[16]) {
+    float4* o = reinterpret_cast<float4*>(base);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[(int64_t)(4 * half + q) * N + n] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  };
+
+  const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
+  for (int64_t t = (int64_t)blockIdx.x * 2 + grp; t < ntiles; t += (int64_t)gridDim.x * 2) {
+    const int64_t n = t * 128 + row;
+    const bool valid = n < N;
+    Sample sp;
+    sp.pf[0] = sp.pf[1] = sp.pf[2] = 0.f; sp.xn[0] = sp.xn[1] = sp.xn[2] = 0.f; sp.inside = true;
+    if (valid) load_sample(a.pts, n, a.nb, a.mb, sp);
+    const unsigned vm = __ballot_sync(kFull, valid);
+    float go[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const float4 g = reinterpret_cast<const float4*>(a.g_raw)[n];
+      if (NOUT == 4) { go[0] = g.x; go[1] = g.y; go[2] = g.z; }
+      else go[0] = (a.apply_mask && !sp.inside) ? 0.f : g.w;
+    }
+    if (WS && valid && half == 0) {
+      reinterpret_cast<float4*>(a.GO)[n] = make_float4(go[0], go[1], go[2], go[3]);
+      a.P32[n] = sp.pf[0]; a.P32[N + n] = sp.pf[1]; a.P32[2 * N + n] = sp.pf[2];
+    }
+    float gh[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) s = fmaf(sm[S_WO + o * 32 + col0 + j], go[o], s);
+      gh[j] = s;
+    }
+    // the previous tile's scatter phase used the A buffer as a scratch tile: all of the group must be done with it
+    group_bar();
+#pragma unroll 1
+    for (int l = 4; l >= 0; --l) {
+      if (WS && valid) stash_half(a.GH + (int64_t)l * 32 * N, N, n, gh);
+      if (GRID_GRAD || NEED_DP) {
+        store_half_row(gh);
+        publish_issue([&] { mma(0u, O_WCT + (uint32_t)l * 2u * kBB, kBB, idesc32, l < 4 ? 1u : 0u); });
+      }
+      const uint32_t bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)l * N + n) * 2 + half] : 0u;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gh[j] = ((bits >> j) & 1u) ? gh[j] : 0.f;
+      if (WS && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);
+      if (GRID_GRAD || NEED_DP) wait_mma();
+      if (l > 0 || EMB) {
+        store_half_row(gh);
+        publish_issue([&] {
+          if (l == 4) mma(32u, O_WT + 6 * kBB, kBB, idesc32, 0u);
+          else if (l == 3) { mma(32u, O_WT + 4 * kBB, kBB, idesc32, 0u); if (EMB) mma(64u, O_W3ET, kBE, idesc96, 0u); }
+          else if (l == 2) mma(32u, O_WT + 2 * kBB, kBB, idesc32, 0u);
+          else if (l == 1) mma(32u, O_WT, kBB, idesc32, 0u);
+          else mma(64u, O_W0T, kBE, idesc96, 1u);
+        });
+        wait_mma();
+        if (l > 0) tmem_ld16(tm_lane + 32u + col0, gh);
+      }
+    }
+    // ---- Fourier embedding: gradient at the arguments, point gradient, dB scratch
+    float gp[3] = {0.f, 0.f, 0.f};
+    if (EMB) {
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        float ge[16];
+        tmem_ld16(tm_lane + 64u + 32u * c + col0, ge);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int kk = 32 * c + col0 + k;
+          const float bx = sm[S_B + kk], by = sm[S_B + 96 + kk], bz = sm[S_B + 192 + kk];
+          const float garg = ge[k] * fourier_cos(fmaf(sp.pf[2], bz, fmaf(sp.pf[1], by, sp.pf[0] * bx)));
+          ge[k] = garg;
+          gp[0] = fmaf(bx, garg, gp[0]); gp[1] = fmaf(by, garg, gp[1]); gp[2] = fmaf(bz, garg, gp[2]);
+        }
+        if (WS && valid) {
+          float4* o = reinterpret_cast<float4*>(a.GARG);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o[(int64_t)(8 * c + 4 * half + q) * N + n] = make_float4(ge[4 * q], ge[4 * q + 1], ge[4 * q + 2], ge[4 * q + 3]);
+        }
+      }
+    }
+    // ---- feature gradient: TMEM -> scratch tile [row][channel] -> warp-cooperative scatter
+    if (GRID_GRAD || NEED_DP) {
+      float gc[16];
+      tmem_ld16(tm_lane + col0, gc);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gtile[row * kTileLd + col0 + j] = gc[j];
+      umma::tc_fence_before();
+      group_bar();
+      // warp (quarter, half) scatters rows 32*quarter + 16*half + [0,16); lane = channel
+      const GridDev& g = a.ga;
+      const float ux = unnormalise(sp.xn[0], g.W), uy = unnormalise(sp.xn[1], g.H), uz = unnormalise(sp.xn[2], g.D);
+      const float* gd = g.data + lane;
+      int64_t run_base = -1;
+      unsigned run_ok = 0;
+      float run[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) run[k] = 0.f;
+      float dux = 0.f, duy = 0.f, duz = 0.f;
+      for (int i = 0; i < 16; ++i) {
+        const int src = 16 * half + i;
+        const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
+        if (!((vm >> src) & 1u)) continue;
+        const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
+        const float gcv = gtile[(quarter * 32 + src) * kTileLd + lane];
+        if (GRID_GRAD) {
+          if (c.base != run_base) {
+            if (run_base >= 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if ((run_ok >> k) & 1u) atomicAdd(a.g_grid + run_base + corner_offset(k, g.W, g.H) + lane, run[k]);
+            }
+            run_base = c.base; run_ok = c.ok;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) run[k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) run[k] = fmaf(corner_weight(c, k), gcv, run[k]);
+        }
+        if (NEED_DP) {
+          float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if ((c.ok >> k) & 1u) {
+              const float v = __ldg(gd + c.base + corner_offset(k, g.W, g.H));
+              const float wx = c.wx[k & 1], wy = c.wy[(k >> 1) & 1], wz = c.wz[k >> 2];
+              gx += ((k & 1) ? v : -v) * wy * wz;
+              gy += (((k >> 1) & 1) ? v : -v) * wx * wz;
+              gz += ((k >> 2) ? v : -v) * wx * wy;
+            }
+          }
+          gx = warp_sum(gx * gcv); gy = warp_sum(gy * gcv); gz = warp_sum(gz * gcv);
+          if (lane == src) { dux = gx * c.gm[0]; duy = gy * c.gm[1]; duz = gz * c.gm[2]; }
+        }
+      }
+      if (GRID_GRAD && run_base >= 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if ((run_ok >> k) & 1u) atomicAdd(a.g_grid + run_base + corner_offset(k, g.W, g.H) + lane, run[k]);
+      }
+      if (NEED_DP) {
+        // rows 16*half..16*half+15 of this quarter got their grid-path gradient in lanes 16*half + i of THIS warp;
+        // combine with the embedding path: half 0 holds gp of its own columns, half 1 left its share in the tile
+        const bool mine = (lane >> 4) == half;   // this lane's row was scattered by this warp
+        if (mine && valid) {
+          gp[0] += norm_grad(a.pts, a.nb, 0, dux); gp[1] += norm_grad(a.pts, a.nb, 1, duy); gp[2] += norm_grad(a.pts, a.nb, 2, duz);
+        }
+        if (valid) {
+          // each (row, half) thread adds its partial sum; float atomics on 3 words per row, 2 adders per word
+          float* o = a.g_pts + 3 * n;
+          atomicAdd(o, gp[0]); atomicAdd(o + 1, gp[1]); atomicAdd(o + 2, gp[2]);
+        }
+      }
+    } else if (NEED_DP && valid) {
+      float* o = a.g_pts + 3 * n;
+      atomicAdd(o, gp[0]); atomicAdd(o + 1, gp[1]); atomicAdd(o + 2, gp[2]);
+    }
+    umma::tc_fence_before();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem_base_s, 512);
+}
+
 template <int CD, int NOUT, bool GG, bool DP, bool WS>
 int launch_bwd_t(const BwdArgs& a, cudaStream_t st) {
+  if (use_tensor_cores()) {
+    auto kern = k_grid_mlp_bwd_tc<CD, NOUT, GG, DP, WS>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmem);
+    const int64_t pairs = ((a.pts.N + 127) / 128 + 1) / 2;
+    const int grid = (int)((pairs < (int64_t)sm_count()) ? pairs : (int64_t)sm_count());
+    kern<<<grid, 512, tcb::kSmem, st>>>(a);
+    return launch_status("k_grid_mlp_bwd_tc");
+  }
   auto kern = k_grid_mlp_bwd<CD, NOUT, GG, DP, WS>;
   const size_t sm = (size_t)(wfloats<CD>() + 32 * kLdc) * sizeof(float);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -108,7 +108,7 @@ __global__ void k_imap_embed(pn_points pts, Bound6 nb, Bound6 mb, const float* _
   if (P32 && lane < 3) P32[(int64_t)lane * pts.N + n] = sp.pf[lane];
   for (int k = lane; k < 96; k += 32) {
     float v = 0.f;
-    if (k < PN_EMBED) v = sinf(fmaf(sp.pf[2], Bs[2 * PN_EMBED + k], fmaf(sp.pf[1], Bs[PN_EMBED + k], sp.pf[0] * Bs[k])));
+    if (k < PN_EMBED) v = fourier_sin(fmaf(sp.pf[2], Bs[2 * PN_EMBED + k], fmaf(sp.pf[1], Bs[PN_EMBED + k], sp.pf[0] * Bs[k])));
     E[n * 96 + k] = v;
   }
 }
@@ -174,7 +174,7 @@ __global__ void k_imap_embed_bwd(pn_points pts, Bound6 nb, Bound6 mb, const floa
     float ga = 0.f;
     if (k < PN_EMBED) {
       const float arg = fmaf(sp.pf[2], Bs[2 * PN_EMBED + k], fmaf(sp.pf[1], Bs[PN_EMBED + k], sp.pf[0] * Bs[k]));
-      ga = GE[n * 96 + k] * cosf(arg);
+      ga = GE[n * 96 + k] * fourier_cos(arg);
       gp[0] = fmaf(Bs[k], ga, gp[0]); gp[1] = fmaf(Bs[PN_EMBED + k], ga, gp[1]); gp[2] = fmaf(Bs[2 * PN_EMBED + k], ga, gp[2]);
     }
     GE[n * 96 + k] = ga;

@@ -124,6 +124,21 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint3
   }
 }
 
+// Same product with descriptors prepared once: a_hi/a_lo/b_hi/b_lo are descriptors of the
+// operands' first K-step; a K-step of 8 advances the 14-bit start-address field by
+// 2*LBO/16 (no carry into the LBO field for any shared-memory address).  K = 32.
+__device__ __forceinline__ void mma_3xtf32_k32(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                               uint32_t a_step, uint32_t b_step, uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t ah = a_hi + (uint64_t)(ks * a_step), al = a_lo + (uint64_t)(ks * a_step);
+    const uint64_t bh = b_hi + (uint64_t)(ks * b_step), bl = b_lo + (uint64_t)(ks * b_step);
+    mma_tf32(d_tmem, al, bh, idesc, ks == 0 ? accumulate : 1u);
+    mma_tf32(d_tmem, ah, bl, idesc, 1u);
+    mma_tf32(d_tmem, ah, bh, idesc, 1u);
+  }
+}
+
 // ---- TMEM -> registers: 32 consecutive columns of this thread's lane ----------------------
 // taddr: (lane << 16) | column; a warp may only touch lanes [32*(warp%4), +32).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
