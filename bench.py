@@ -166,7 +166,9 @@ def run_ours(args):
         renderer.depth_max_override = D.share_depth_max(gd) if world > 1 else None
         depth, var, color = renderer.render_batch_ray(grids, model, rd, ro, dev, "color", gt_depth=gd)
         m = gd > 0
-        loss = torch.abs(gd[m] - depth[m]).sum() + W_COLOR * torch.abs(gc - color).sum()
+        # Mapper.py:641-646 (masked L1 depth + weighted L1 colour), written without boolean indexing so that
+        # the host does not synchronise in the middle of the step
+        loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
         loss.backward()
         D.allreduce_gradients([t.grad for t in trained])
         out = loss.item() if e2e else None  # device -> host read of the step's result

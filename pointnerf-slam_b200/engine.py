@@ -328,7 +328,7 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                                                 C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
                                                 C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_grid_mlp_bwd")
                 if want_w[i]:
-                    gp = [torch.zeros_like(t) for t in p.params]
+                    gp = zeros_like_flat(p.params)
                     g = L.PnGridMlpGrad()
                     g.B = gp[0].data_ptr()
                     for k in range(5):
@@ -348,7 +348,7 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                                               C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
                                               C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_coarse_mlp_bwd")
                 if want_w[i]:
-                    gp = [torch.zeros_like(t) for t in p.params]
+                    gp = zeros_like_flat(p.params)
                     g = L.PnCoarseMlpGrad()
                     for k in range(5):
                         g.W[k] = gp[k].data_ptr(); g.b[k] = gp[5 + k].data_ptr()
@@ -359,6 +359,18 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                 else:
                     g_params.append(None)
     return g_grids, g_pts, g_params
+
+
+def zeros_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Zeroed gradient sinks for a list of parameters, carved out of ONE buffer (one
+    memset launch instead of one per parameter; every view stays 16-byte aligned)."""
+    sizes = [(t.numel() + 3) // 4 * 4 for t in tensors]
+    flat = torch.zeros(sum(sizes), dtype=tensors[0].dtype, device=tensors[0].device)
+    out, off = [], 0
+    for t, sz in zip(tensors, sizes):
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += sz
+    return out
 
 
 def _grad_flags(plan: Plan, needs: Sequence[bool], n_lead: int, freeze_map: bool):

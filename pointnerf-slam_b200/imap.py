@@ -60,7 +60,8 @@ def backward(p, pts, g_raw: torch.Tensor, stash: ImapStash, g_pts: Optional[torc
     GA, GB, GO = torch.empty(n * width, **f32), torch.empty(n * width, **f32), torch.empty(n * 4, **f32)
     gp = g = None
     if want_w:
-        gp = [torch.zeros_like(t) for t in p.params]
+        from .engine import zeros_like_flat
+        gp = zeros_like_flat(p.params)
         nb = m.n_blocks
         g = PnImapMlpGrad()
         g.B = gp[0].data_ptr()

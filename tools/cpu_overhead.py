@@ -31,7 +31,7 @@ def step():
     ro, rd, gd, gc = torch.cat(ro), torch.cat(rd), torch.cat(gd), torch.cat(gc)
     depth, var, color = r.render_batch_ray(grids, model, rd, ro, dev, "color", gt_depth=gd)
     m = gd > 0
-    loss = torch.abs(gd[m] - depth[m]).sum() + 0.2 * torch.abs(gc - color).sum()
+    loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + 0.2 * torch.abs(gc - color).sum()
     loss.backward()
     for t in trained: t.grad = None
 for _ in range(5): step()
