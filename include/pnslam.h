@@ -116,7 +116,7 @@ enum { PN_OUT_SET_ALL = 0, /* raw[n] = (0,0,0,occ) or the 4 colour-decoder outpu
 
 const char* pn_last_error(void);
 int pn_version(void);
-/* number of kernels this thread has launched through the library (for bench accounting) */
+/* number of kernels this process has launched through the library (for bench accounting) */
 long long pn_launch_count(void);
 
 /* -------- pose and ray generation (src/common.py:74-176, 248-266) -------- */

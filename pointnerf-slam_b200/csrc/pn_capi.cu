@@ -1,5 +1,7 @@
 // Error reporting and device queries shared by all C-ABI entry points.
 #include <stdarg.h>
+
+#include <atomic>
 #include <stdio.h>
 
 #include "pn_common.cuh"
@@ -7,7 +9,7 @@
 namespace pn {
 namespace {
 thread_local char g_err[512] = "";
-thread_local long long g_launches = 0;  // kernels launched by this thread through the C ABI
+std::atomic<long long> g_launches{0};  // kernels launched through the C ABI (autograd's backward runs on another thread)
 }
 
 void set_error(const char* fmt, ...) {
@@ -36,4 +38,4 @@ int sm_count() {
 
 extern "C" const char* pn_last_error(void) { return pn::g_err; }
 extern "C" int pn_version(void) { return 100; }
-extern "C" long long pn_launch_count(void) { return pn::g_launches; }
+extern "C" long long pn_launch_count(void) { return pn::g_launches.load(); }

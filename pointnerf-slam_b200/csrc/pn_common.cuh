@@ -24,6 +24,9 @@ constexpr unsigned kFull = 0xffffffffu;
 void set_error(const char* fmt, ...);
 int launch_status(const char* what);   // cudaGetLastError -> 0 / 1 (+message)
 int sm_count();
+// tensor-core weight gradients (pn_wgrad_tc.cu): 0 ok, 1 error, -1 not applicable
+int launch_wgrad_tc(int64_t N, int c_dim, const float* H, const float* C, const float* E, const float* GA, const float* GH,
+                    float* const* W, float* const* b, float* const* Wc, float* const* bc, cudaStream_t st);
 
 struct Bound6 {  // [lo_x hi_x lo_y hi_y lo_z hi_z]
   double v[6];

@@ -1531,6 +1531,11 @@ extern "C" int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash
       add(GH, stash->C + c * blk, g->Wc[l] ? g->Wc[l] + 32 * c : nullptr, c == 0 ? g->bc[l] : nullptr, cd, 32);
   }
   a.nmats = nm;
+  if (nm > 0 && use_tensor_cores()) {  // all W / b / Wc / bc sinks present -> tensor-core GEMMs
+    const int rc = launch_wgrad_tc(N, cd, stash->H, stash->C, stash->E, ws->GA, ws->GH, g->W, g->b, g->Wc, g->bc, st);
+    if (rc > 0) return 1;
+    if (rc == 0) nm = 0;
+  }
   if (nm > 0) {
     int64_t tiles = (N + kThreads - 1) / kThreads;
     int split = (int)((2 * sm_count() + nm - 1) / nm);
