@@ -86,13 +86,13 @@ def allreduce_gradients(tensors: Iterable[Optional[torch.Tensor]], small_bytes: 
         works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
     if small:
         dtype = small[0].dtype
-        bucket = torch.cat([t.reshape(-1).to(dtype) for t in small])
+        bucket = torch.cat([t.reshape(-1).to(dtype) for t in small])        # one launch
         dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
-        off = 0
+        views, off = [], 0
         for t in small:
-            n = t.numel()
-            t.copy_(bucket[off:off + n].reshape(t.shape))
-            off += n
+            views.append(bucket[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+        torch._foreach_copy_(small, views)                                   # one (fused) launch back
     for w in works:
         w.wait()
     for dst, tmp in copies:
