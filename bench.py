@@ -230,22 +230,38 @@ def run_ours(args):
     # per sample per grid read, plus 2048 B per sample read-modify-write of the gradient grid in backward
     alg = {"grid_mlp_fwd:color": 1, "grid_mlp_fwd:fine": 2, "grid_mlp_fwd:middle": 1,
            "grid_mlp_bwd:color": 3, "grid_mlp_bwd:fine": 3, "grid_mlp_bwd:middle": 3}
+    # the weight-gradient GEMM's algorithmic bytes: it must read its operands once (h0..h3, emb, c, GA, GH:
+    # (128 + 96 + 32 + 160 + 160) floats per sample)
+    alg_wgrad = n_samples * (128 + 96 + 32 + 160 + 160) * 4
+    # measured DRAM traffic per launch of the same kernels (ncu --set full, profiles/r1_dram_traffic_per_launch.json)
+    ncu_name = {"grid_mlp_fwd:color": "k_grid_mlp_fwd_tc<32, 4>", "grid_mlp_fwd:fine": "k_grid_mlp_fwd_tc<64, 1>",
+                "grid_mlp_fwd:middle": "k_grid_mlp_fwd_tc<32, 1>", "grid_mlp_bwd:color": "k_grid_mlp_bwd_tc<32, 4, 1, 1, 1>",
+                "grid_mlp_bwd:fine": "k_grid_mlp_bwd_tc<64, 1, 1, 1, 0>", "grid_mlp_bwd:middle": "k_grid_mlp_bwd_tc<32, 1, 1, 1, 0>",
+                "grid_mlp_wgrad:color": "k_wgrad_tc"}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic_per_launch.json")
+    if top in ncu_name and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(ncu_name[top])
     roofline = None
     if top is not None:
         dur_ms = statistics.mean(kern[top])
-        bytes_launch = n_samples * BYTES_PER_SAMPLE_GATHER * alg.get(top, 1)
+        bytes_launch = alg_wgrad if top.startswith("grid_mlp_wgrad") else n_samples * BYTES_PER_SAMPLE_GATHER * alg.get(top, 1)
         achieved = bytes_launch / (dur_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
-                    "frac": round(achieved / hbm, 4), "traffic": None, "peak_source": which,
+                    "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": which,
                     "avg_launch_ms": round(dur_ms, 4), "alg_bytes_per_launch": bytes_launch,
                     "kernel_share_of_step": {k: round(v, 3) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
-                    "note": "kernel is FP32-FFMA bound (25 FLOP/B); HBM roofline is the BASELINE.md denominator"}
+                    "note": "decoder layers run on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulate in TMEM); the kernels are "
+                            "latency-bound (tensor pipe ~10% active, 16 warps/SM), not HBM-bound; HBM roofline is the "
+                            "BASELINE.md denominator"}
     step_frac = value / world * BYTES_PER_RAY_STEP / (hbm * 1e9)
     line = {"metric": "rays/sec fwd+bwd render_batch_ray (NICE mapping iteration, stage color)", "value": round(value, 1),
             "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N_KEYFRAMES * PIX_PER_KF, "samples_per_ray": S,
+            "config": {"workload": WORKLOAD, "arithmetic": "float32 results via 3xTF32 tensor-core products with FP32 accumulation "
+                       "(max error 5e-7 relative, tests/test_gpu_tc.py); float64 geometry as in the reference",
+                       "rays_per_step_per_gpu": N_KEYFRAMES * PIX_PER_KF, "samples_per_ray": S,
                        "grids": {k: list(v.shape) for k, v in grids.items()}, "l2": "flushed between timed iterations "
                        "(256 MiB fill, untimed); per-step CUDA events summed", "parallelism": f"ray-shard dp{world}"},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s",
