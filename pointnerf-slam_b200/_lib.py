@@ -148,16 +148,62 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+def _dev_index(device) -> int:
+    if isinstance(device, int):
+        return device
+    idx = getattr(device, "index", None)
+    if idx is None:
+        idx = torch.device(device).index
+    return torch.cuda.current_device() if idx is None else idx
+
+
 def stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's CURRENT stream on the device (queried every call: callers
+    may switch streams between calls)."""
+    return torch._C._cuda_getCurrentRawStream(_dev_index(device))
+
+
+class device_guard:
+    """``with device_guard(dev):`` makes dev the current CUDA device only when it is not already
+    (the common case costs one integer comparison instead of two cudaSetDevice calls)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = _dev_index(device)
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+
+_bound_cache = {}
 
 
 def f64x6(bound) -> C.Array:
-    """(3,2) bound -> host double[6] = [lo_x hi_x lo_y hi_y lo_z hi_z]."""
+    """(3,2) bound -> host double[6] = [lo_x hi_x lo_y hi_y lo_z hi_z].  Host-side values are
+    memoised per tensor object and in-place version (a bound is set once by the orchestrator)."""
     if isinstance(bound, torch.Tensor):
+        key = (id(bound), bound._version, bound.data_ptr())
+        hit = _bound_cache.get(key)
+        if hit is not None:
+            return hit
         vals = bound.detach().to("cpu", torch.float64).reshape(-1).tolist()
-    else:
-        vals = [float(v) for row in bound for v in row]
+        if len(_bound_cache) > 64:
+            _bound_cache.clear()
+        arr = (C.c_double * 6)(*vals)
+        _bound_cache[key] = arr
+        return arr
+    vals = [float(v) for row in bound for v in row]
     return (C.c_double * 6)(*vals)
 
 

@@ -40,7 +40,7 @@ class _CameraFn(torch.autograd.Function):
         camc = cam.detach().float().contiguous()
         B = camc.shape[0]
         out = torch.empty((B, 3, 4), dtype=torch.float32, device=cam.device)
-        with torch.cuda.device(cam.device):
+        with L.device_guard(cam.device):
             L.check(L.lib().pn_camera_from_tensor_fwd(C.c_void_p(camc.data_ptr()), B, C.c_void_p(out.data_ptr()),
                                                       C.c_void_p(L.stream_ptr(cam.device))), "pn_camera_from_tensor_fwd")
         ctx.save_for_backward(camc)
@@ -51,7 +51,7 @@ class _CameraFn(torch.autograd.Function):
         (camc,) = ctx.saved_tensors
         g = g.float().contiguous()
         out = torch.empty_like(camc)
-        with torch.cuda.device(camc.device):
+        with L.device_guard(camc.device):
             L.check(L.lib().pn_camera_from_tensor_bwd(C.c_void_p(camc.data_ptr()), C.c_void_p(g.data_ptr()), camc.shape[0],
                                                       C.c_void_p(out.data_ptr()), C.c_void_p(L.stream_ptr(camc.device))),
                     "pn_camera_from_tensor_bwd")
@@ -114,7 +114,7 @@ class _SampleRaysFn(torch.autograd.Function):
         rd = torch.empty((n, 3), dtype=torch.float32, device=dev)
         d_out = torch.empty(n, dtype=torch.float32, device=dev) if depth is not None else None
         c_out = torch.empty((n, 3), dtype=color.dtype, device=dev) if color is not None else None
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(L.lib().pn_sample_rays_fwd(C.c_void_p(idx.data_ptr()), n, H0, W0, Wc, W, f32(fx), f32(fy), f32(cx), f32(cy),
                                                C.c_void_p(c2wc.data_ptr()), c2wc.shape[-1], C.c_void_p(L.ptr(depth)),
                                                C.c_void_p(L.ptr(color)), int(color is not None and color.dtype == torch.float64),
@@ -132,7 +132,7 @@ class _SampleRaysFn(torch.autograd.Function):
         g = torch.zeros((3, 4), dtype=torch.float32, device=dev)
         g_ro = g_ro.float().contiguous() if g_ro is not None else None
         g_rd = g_rd.float().contiguous() if g_rd is not None else None
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(L.lib().pn_rays_bwd(C.c_void_p(idx.data_ptr()), idx.shape[0], H0, W0, Wc, f32(fx), f32(fy), f32(cx), f32(cy),
                                         C.c_void_p(L.ptr(g_ro)), C.c_void_p(L.ptr(g_rd)), C.c_void_p(g.data_ptr()),
                                         C.c_void_p(L.stream_ptr(dev))), "pn_rays_bwd")
@@ -170,7 +170,7 @@ class _ImageRaysFn(torch.autograd.Function):
         c2wc = c2w.detach().float().contiguous()
         ro = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         rd = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(L.lib().pn_image_rays_fwd(H, W, f32(fx), f32(fy), f32(cx), f32(cy), C.c_void_p(c2wc.data_ptr()),
                                               c2wc.shape[-1], C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()),
                                               C.c_void_p(L.stream_ptr(dev))), "pn_image_rays_fwd")
@@ -184,7 +184,7 @@ class _ImageRaysFn(torch.autograd.Function):
         g = torch.zeros((3, 4), dtype=torch.float32, device=dev)
         g_ro = g_ro.float().contiguous() if g_ro is not None else None
         g_rd = g_rd.float().contiguous() if g_rd is not None else None
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(L.lib().pn_rays_bwd(None, H * W, 0, 0, W, f32(fx), f32(fy), f32(cx), f32(cy), C.c_void_p(L.ptr(g_ro)),
                                         C.c_void_p(L.ptr(g_rd)), C.c_void_p(g.data_ptr()), C.c_void_p(L.stream_ptr(dev))),
                     "pn_rays_bwd")
@@ -235,7 +235,7 @@ class _CompositeFn(torch.autograd.Function):
         gv = g_var.double().contiguous() if g_var is not None else None
         gc = g_rgb.float().contiguous() if g_rgb is not None else None
         g_rd = torch.zeros_like(rdc) if (ctx.needs_input_grad[2] and not ctx.occupancy) else None
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(L.lib().pn_composite_bwd(C.c_void_p(rawc.data_ptr()), C.c_void_p(zc.data_ptr()), C.c_void_p(rdc.data_ptr()),
                                              C.c_int64(R), S, int(ctx.occupancy), C.c_void_p(L.ptr(gd)), C.c_void_p(L.ptr(gv)),
                                              C.c_void_p(L.ptr(gc)), C.c_void_p(g_raw.data_ptr()), C.c_void_p(L.ptr(g_rd)),
@@ -262,7 +262,7 @@ def sample_pdf(bins, weights, N_samples, det=False, device='cuda:0'):
         u_lin, u_rand = torch.linspace(0., 1., steps=N_samples).to(dev), None
     else:
         u_lin, u_rand = None, torch.rand((R, N_samples)).to(dev).contiguous()
-    with torch.cuda.device(dev):
+    with L.device_guard(dev):
         L.check(L.lib().pn_sample_pdf(C.c_void_p(b.data_ptr()), C.c_void_p(w.data_ptr()), C.c_int64(R), nb, N_samples,
                                       C.c_void_p(L.ptr(u_lin)), C.c_void_p(L.ptr(u_rand)), C.c_void_p(out.data_ptr()),
                                       C.c_void_p(L.stream_ptr(dev))), "pn_sample_pdf")

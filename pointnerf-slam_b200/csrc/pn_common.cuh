@@ -153,7 +153,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// sin / cos of a Fourier argument (|x| up to a few thousand rad): two-constant Cody-Waite
+// sin / cos of a Fourier argument (branch-free; |x| up to ~1e5 rad, far beyond any p.B of a scene): two-constant Cody-Waite
 // reduction to [-pi, pi] followed by the SFU approximation.  Absolute error <= ~5e-7, an
 // order of magnitude below the float32 rounding noise of the argument p.B itself (>= 1e-5
 // at |x| ~ 100), at a fifth of the instructions of libdevice sinf.
@@ -162,12 +162,8 @@ __device__ __forceinline__ float reduce_2pi(float x) {
   float r = fmaf(n, -6.2831854820251465f, x);
   return fmaf(n, 1.7484555e-7f, r);
 }
-__device__ __forceinline__ float fourier_sin(float x) {
-  return fabsf(x) < 16384.f ? __sinf(reduce_2pi(x)) : sinf(x);
-}
-__device__ __forceinline__ float fourier_cos(float x) {
-  return fabsf(x) < 16384.f ? __cosf(reduce_2pi(x)) : cosf(x);
-}
+__device__ __forceinline__ float fourier_sin(float x) { return __sinf(reduce_2pi(x)); }
+__device__ __forceinline__ float fourier_cos(float x) { return __cosf(reduce_2pi(x)); }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 

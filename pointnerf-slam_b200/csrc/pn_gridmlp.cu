@@ -755,7 +755,9 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
     umma::tc_fence_before();
     asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
     if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
-    umma::mbar_wait(bar, phase);
+    // one lane polls the mbarrier; the other 255 threads of the group sleep on a named barrier
+    if ((tid & 255) < 32) { if (lane == 0) umma::mbar_wait(bar, phase); __syncwarp(); }
+    asm volatile("bar.sync %0, 256;" ::"r"(grp + 4) : "memory");
     phase ^= 1u;
     umma::tc_fence_after();
   };
@@ -955,6 +957,7 @@ int launch_fwd(const FwdArgs& a, cudaStream_t st) {
 //    64..159  D_ge = ga_3 . W3[:, :93] + ga_0 . W0  (gradient at the Fourier embedding)
 namespace tcb {
 using tc::kLbo; using tc::kASbo; using tc::kABytes;
+constexpr int kGroups = 3;                     // independent 128-sample tiles in flight per CTA (160 TMEM columns each)
 constexpr uint32_t kBB = 4096;                 // one [32 x 32] operand copy
 constexpr uint32_t kBE = 12288;                // one [96 x 32] operand copy
 constexpr uint32_t O_WT = 0;                   // W1^T, W2^T, W3h^T, W4^T (hi, lo each)
@@ -962,9 +965,9 @@ constexpr uint32_t O_WCT = O_WT + 8 * kBB;     // Wc_l[:, :32]^T, l = 0..4
 constexpr uint32_t O_W0T = O_WCT + 10 * kBB;   // W0^T  [96 x 32]
 constexpr uint32_t O_W3ET = O_W0T + 2 * kBE;   // W3[:, :93]^T
 constexpr uint32_t O_A = O_W3ET + 2 * kBE;     // 2 groups x (hi, lo)
-constexpr uint32_t O_SMALL = O_A + 4 * kABytes;
+constexpr uint32_t O_SMALL = O_A + kGroups * 2 * kABytes;
 constexpr int S_B = 0, S_WO = 288, S_TOTAL = 416;  // floats
-constexpr uint32_t kSmem = O_SMALL + S_TOTAL * 4u + 24u;
+constexpr uint32_t kSmem = O_SMALL + S_TOTAL * 4u + 40u;
 constexpr int kTileLd = 33;                    // padded row of the feature-gradient tile (reuses the A buffer)
 
 // B operand = transpose of a row-major [32 x ld] weight block: element (n, j) = src[j*ld + col0 + n], n < nrows
@@ -984,7 +987,7 @@ __device__ __forceinline__ void stage_bt(unsigned char* hi, uint32_t copy_bytes,
 }  // namespace tcb
 
 template <int CD, int NOUT, bool GRID_GRAD, bool NEED_DP, bool WS>
-__global__ void __launch_bounds__(512, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
+__global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using namespace tcb;
   constexpr bool EMB = NEED_DP || WS;
@@ -993,12 +996,12 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
   const int row = quarter * 32 + lane, col0 = 16 * half;
   float* sm = reinterpret_cast<float*>(smraw + O_SMALL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S_TOTAL);
-  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 4);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 8);
   unsigned char* a_hi = smraw + O_A + (uint32_t)grp * 2u * kABytes;
   unsigned char* a_lo = a_hi + kABytes;
   float* gtile = reinterpret_cast<float*>(a_hi);   // [128][33] floats, valid between the last MMA and the next tile
   if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
-  if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
+  if (tid == 0) { for (int i = 0; i < kGroups; ++i) umma::mbar_init(&bars[i], 1); umma::fence_mbar_init(); }
   stage_bt(smraw + O_WT, kBB, a.w.W[1], 32, 0, 32, 32);
   stage_bt(smraw + O_WT + 2 * kBB, kBB, a.w.W[2], 32, 0, 32, 32);
   stage_bt(smraw + O_WT + 4 * kBB, kBB, a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
@@ -1008,13 +1011,13 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
     stage_bt(smraw + O_W0T, kBE, a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
     stage_bt(smraw + O_W3ET, kBE, a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
   }
-  for (int i = tid; i < 288; i += 512) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
-  for (int i = tid; i < 128; i += 512) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
+  for (int i = tid; i < 288; i += blockDim.x) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
+  for (int i = tid; i < 128; i += blockDim.x) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
   umma::fence_proxy_async();
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
-  const uint32_t tm = tmem_base_s + (uint32_t)grp * 256u;
+  const uint32_t tm = tmem_base_s + (uint32_t)grp * 160u;
   const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);
   const uint32_t sA = umma::smem_u32(a_hi), sW = umma::smem_u32(smraw);
   constexpr uint32_t idesc32 = umma::instr_desc_tf32(128, 32), idesc96 = umma::instr_desc_tf32(128, 96);
@@ -1034,7 +1037,12 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
     group_bar();
     if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
   };
-  auto wait_mma = [&] { umma::mbar_wait(bar, phase); phase ^= 1u; umma::tc_fence_after(); };
+  auto wait_mma = [&] {   // one lane polls the mbarrier; the rest of the group sleeps on a named barrier
+    if ((tid & 255) < 32) { if (lane == 0) umma::mbar_wait(bar, phase); __syncwarp(); }
+    asm volatile("bar.sync %0, 256;" ::"r"(grp + 4) : "memory");
+    phase ^= 1u;
+    umma::tc_fence_after();
+  };
   auto store_half_row = [&](const float (&v)[16]) {
     const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)(4 * half) * kLbo;
 #pragma unroll
@@ -1053,7 +1061,7 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
   };
 
   const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
-  for (int64_t t = (int64_t)blockIdx.x * 2 + grp; t < ntiles; t += (int64_t)gridDim.x * 2) {
+  for (int64_t t = (int64_t)blockIdx.x * kGroups + grp; t < ntiles; t += (int64_t)gridDim.x * kGroups) {
     const int64_t n = t * 128 + row;
     const bool valid = n < N;
     Sample sp;
@@ -1216,9 +1224,9 @@ int launch_bwd_t(const BwdArgs& a, cudaStream_t st) {
   if (use_tensor_cores()) {
     auto kern = k_grid_mlp_bwd_tc<CD, NOUT, GG, DP, WS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmem);
-    const int64_t pairs = ((a.pts.N + 127) / 128 + 1) / 2;
+    const int64_t pairs = ((a.pts.N + 127) / 128 + tcb::kGroups - 1) / tcb::kGroups;
     const int grid = (int)((pairs < (int64_t)sm_count()) ? pairs : (int64_t)sm_count());
-    kern<<<grid, 512, tcb::kSmem, st>>>(a);
+    kern<<<grid, tcb::kGroups * 256, tcb::kSmem, st>>>(a);
     return launch_status("k_grid_mlp_bwd_tc");
   }
   auto kern = k_grid_mlp_bwd<CD, NOUT, GG, DP, WS>;

@@ -163,7 +163,7 @@ def grid_channels_last(g: torch.Tensor) -> torch.Tensor:
         return g
     src = g.detach().contiguous()
     out = torch.empty_like(src, memory_format=torch.channels_last_3d)
-    with torch.cuda.device(g.device):
+    with L.device_guard(g.device):
         L.check(L.lib().pn_grid_transpose(C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr()), g.shape[2], g.shape[3],
                                           g.shape[4], 1, C.c_void_p(L.stream_ptr(g.device))), "pn_grid_transpose")
     return out
@@ -264,7 +264,7 @@ def plan_forward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, dev
     st = C.c_void_p(L.stream_ptr(device))
     mb = host_bound(plan.mask_bound) if plan.mask_bound is not None else None
     apply_mask = 1 if mb is not None else 0
-    with torch.cuda.device(device):
+    with L.device_guard(device):
         for i, p in enumerate(plan.passes):
             stash = Stash(p, n, device, bool(want_w[i])) if (save and p.kind != "imap") else None
             stashes.append(stash)
@@ -305,7 +305,7 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
     st = C.c_void_p(L.stream_ptr(device))
     mb = host_bound(plan.mask_bound) if plan.mask_bound is not None else None
     apply_mask = 1 if mb is not None else 0
-    with torch.cuda.device(device):
+    with L.device_guard(device):
         for i, p in enumerate(plan.passes):
             nb = host_bound(p.norm_bound)
             gg = g_grids.get(p.grid_a) if p.grid_a else None

@@ -58,7 +58,7 @@ def composite(raw: torch.Tensor, z: torch.Tensor, rays_d: torch.Tensor, occupanc
     var = torch.empty(R, dtype=torch.float64, device=dev)
     rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
     w = torch.empty((R, S), dtype=torch.float32, device=dev) if want_weights else None
-    with torch.cuda.device(dev):
+    with L.device_guard(dev):
         L.check(L.lib().pn_composite_fwd(C.c_void_p(raw.data_ptr()), C.c_void_p(z.data_ptr()), C.c_void_p(rays_d.data_ptr()),
                                          C.c_int64(R), S, int(occupancy), C.c_void_p(depth.data_ptr()),
                                          C.c_void_p(var.data_ptr()), C.c_void_p(rgb.data_ptr()), C.c_void_p(L.ptr(w)),
@@ -69,7 +69,7 @@ def composite(raw: torch.Tensor, z: torch.Tensor, rays_d: torch.Tensor, occupanc
 def batch_depth_max(gt: torch.Tensor) -> torch.Tensor:
     """max over the batch of gt_depth as a 1-element device tensor."""
     out = torch.empty(1, dtype=torch.float32, device=gt.device)
-    with torch.cuda.device(gt.device):
+    with L.device_guard(gt.device):
         L.check(L.lib().pn_max_f32(C.c_void_p(gt.data_ptr()), C.c_int64(gt.numel()), C.c_void_p(out.data_ptr()),
                                    C.c_void_p(L.stream_ptr(gt.device))), "pn_max_f32")
     return out
@@ -98,7 +98,7 @@ class RenderRaysFn(torch.autograd.Function):
         z = torch.empty((R, S), dtype=torch.float64, device=dev)
         k = cfg.consts
         tr = t_rand.detach().float().contiguous() if t_rand is not None else None
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.pn_ray_zvals(C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(L.ptr(gt)),
                                      C.c_void_p(L.ptr(depth_max)), C.c_int64(R), E.host_bound(cfg.bound), cfg.n_samples,
                                      n_surface, int(bool(cfg.lindisp)), C.c_void_p(k["t_vals"].data_ptr()),
@@ -115,7 +115,7 @@ class RenderRaysFn(torch.autograd.Function):
         if two_pass:
             S2 = S + cfg.n_importance
             z2 = torch.empty((R, S2), dtype=torch.float64, device=dev)
-            with torch.cuda.device(dev):
+            with L.device_guard(dev):
                 L.check(lib.pn_importance_zvals(C.c_void_p(z.data_ptr()), C.c_void_p(w.data_ptr()), C.c_int64(R), S,
                                                 cfg.n_importance, C.c_void_p(L.ptr(k.get("u_lin"))), None,
                                                 C.c_void_p(z2.data_ptr()), st), "pn_importance_zvals")
@@ -143,7 +143,7 @@ class RenderRaysFn(torch.autograd.Function):
         gc = g_rgb.float().contiguous() if g_rgb is not None else None
         g_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
         g_rd_extra = torch.zeros((R, 3), dtype=torch.float32, device=dev) if (need_rays and not cfg.occupancy) else None
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(lib.pn_composite_bwd(C.c_void_p(ctx.raw.data_ptr()), C.c_void_p(z.data_ptr()), C.c_void_p(rd.data_ptr()),
                                          C.c_int64(R), S, int(cfg.occupancy), C.c_void_p(L.ptr(gd)), C.c_void_p(L.ptr(gv)),
                                          C.c_void_p(L.ptr(gc)), C.c_void_p(g_raw.data_ptr()), C.c_void_p(L.ptr(g_rd_extra)),
@@ -154,7 +154,7 @@ class RenderRaysFn(torch.autograd.Function):
         if need_rays:
             g_o = torch.empty((R, 3), dtype=torch.float32, device=dev)
             g_d = torch.empty((R, 3), dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
+            with L.device_guard(dev):
                 L.check(lib.pn_points_to_rays_bwd(C.c_void_p(g_pts.data_ptr()), C.c_void_p(z.data_ptr()), C.c_int64(R), S,
                                                   C.c_void_p(g_o.data_ptr()), C.c_void_p(g_d.data_ptr()), st),
                         "pn_points_to_rays_bwd")
@@ -226,7 +226,7 @@ class Renderer(object):
         z = torch.empty((R, self.N_samples + n_surface), dtype=torch.float64, device=dev)
         k = self._constants(dev)
         tr = t_rand.detach().float().contiguous().to(dev) if t_rand is not None else None
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(L.lib().pn_ray_zvals(C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(L.ptr(gt)),
                                          C.c_void_p(L.ptr(dmax)), C.c_int64(R), E.host_bound(self.bound), self.N_samples,
                                          n_surface, int(bool(self.lindisp)), C.c_void_p(k["t_vals"].data_ptr()),
@@ -283,7 +283,7 @@ class Renderer(object):
         gt = gt_depth.detach().reshape(-1).float().contiguous()
         pts = torch.empty((R * self.N_samples, 3), dtype=torch.float32, device=dev)
         k = self._constants(dev)
-        with torch.cuda.device(dev):
+        with L.device_guard(dev):
             L.check(L.lib().pn_regulation_points(C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(gt.data_ptr()),
                                                  C.c_void_p(k["t_vals"].data_ptr()), C.c_void_p(t_rand.data_ptr()),
                                                  C.c_int64(R), self.N_samples, C.c_void_p(pts.data_ptr()), None,
