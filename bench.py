@@ -150,6 +150,8 @@ def run_ours(args):
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    reducer = D.OverlappedGradReducer()
+
     def step(e2e=False):
         if e2e:  # host -> device copy of this step's inputs from pinned memory
             frames[0][0].copy_(pinned_depth, non_blocking=True)
@@ -169,8 +171,13 @@ def run_ours(args):
         # Mapper.py:641-646 (masked L1 depth + weighted L1 colour), written without boolean indexing so that
         # the host does not synchronise in the middle of the step
         loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
-        loss.backward()
-        D.allreduce_gradients([t.grad for t in trained])
+        if world > 1:   # all-reduce each gradient as soon as the backward has produced it
+            with reducer:
+                loss.backward()
+            reducer.finish({k: grids[k] for k in ("grid_middle", "grid_fine", "grid_color")},
+                           decoders={"color": model.color_decoder}, others=[c.grad for c in cams[1:]])
+        else:
+            loss.backward()
         out = loss.item() if e2e else None  # device -> host read of the step's result
         for t in trained:
             t.grad = None

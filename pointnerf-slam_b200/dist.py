@@ -101,3 +101,85 @@ def allreduce_gradients(tensors: Iterable[Optional[torch.Tensor]], small_bytes: 
 
 def mapping_gradients(params: Sequence[torch.Tensor]) -> List[Optional[torch.Tensor]]:
     return [p.grad for p in params]
+
+
+class OverlappedGradReducer:
+    """Start the SUM all-reduce of each gradient the moment the backward has produced it.
+
+    Installed as ``engine.GRAD_READY_HOOK`` for the duration of one ``loss.backward()``:
+    the colour grid's gradient is reduced over NVLink while the fine and middle decoder
+    kernels still run, and so on; only the last gradient's reduction is exposed.
+    ``finish()`` waits for the collectives and makes sure every leaf's ``.grad`` holds the
+    reduced values (autograd may have kept the buffer itself or a copy of it).
+
+        red = OverlappedGradReducer()
+        with red:                      # installs / removes the hook
+            loss.backward()
+        red.finish({"grid_color": grids["grid_color"], ...}, decoders={"color": model.color_decoder},
+                   others=[cam.grad for cam in cams])
+    """
+
+    def __init__(self):
+        self.items = []    # (key, tensor or list, flat buffer reduced, work)
+
+    def __enter__(self):
+        from . import engine
+        self._prev = engine.GRAD_READY_HOOK
+        engine.GRAD_READY_HOOK = self._ready
+        return self
+
+    def __exit__(self, *exc):
+        from . import engine
+        engine.GRAD_READY_HOOK = self._prev
+        return False
+
+    def _ready(self, key, grad):
+        if world_size() == 1:
+            return
+        if isinstance(grad, (list, tuple)):           # parameter gradients: views of one flat buffer
+            flat = grad[0]._base if grad[0]._base is not None else None
+            if flat is None or any(g._base is not flat for g in grad):
+                flat = None
+            if flat is not None:
+                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+                self.items.append((key, list(grad), flat, work))
+            else:
+                self.items.append((key, list(grad), None, None))
+            return
+        view = grad.permute(0, 2, 3, 4, 1) if (grad.dim() == 5 and not grad.is_contiguous()) else grad
+        if view.is_contiguous():
+            work = dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True)
+            self.items.append((key, grad, view, work))
+        else:
+            self.items.append((key, grad, None, None))
+
+    def finish(self, grids=None, decoders=None, others=()):
+        """Wait, then reconcile ``.grad`` of the leaves.  ``grids``: key -> leaf tensor;
+        ``decoders``: decoder name -> module whose parameters were trained; ``others``: extra
+        gradient tensors (poses ...) reduced here in one bucket."""
+        late = []
+        for key, grad, buf, work in self.items:
+            if work is not None:
+                work.wait()
+            if isinstance(grad, list):
+                dec = (decoders or {}).get(key[1])
+                leaves = None
+                if dec is not None:
+                    from .engine import grid_mlp_tensors, coarse_mlp_tensors
+                    leaves = grid_mlp_tensors(dec) if hasattr(dec, "fc_c") else coarse_mlp_tensors(dec)
+                if work is None:
+                    late += [p.grad for p in (leaves or []) if p.grad is not None]
+                elif leaves is not None:
+                    dst = [p.grad for p, g in zip(leaves, grad) if p.grad is not None and p.grad.data_ptr() != g.data_ptr()]
+                    src = [g for p, g in zip(leaves, grad) if p.grad is not None and p.grad.data_ptr() != g.data_ptr()]
+                    if dst:
+                        torch._foreach_copy_(dst, src)
+            else:
+                leaf = (grids or {}).get(key)
+                if work is None:
+                    if leaf is not None and leaf.grad is not None:
+                        late.append(leaf.grad)
+                elif leaf is not None and leaf.grad is not None and leaf.grad.data_ptr() != grad.data_ptr():
+                    leaf.grad.copy_(grad)
+        self.items = []
+        allreduce_gradients(list(late) + [t for t in others if t is not None])

@@ -327,6 +327,8 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                     L.check(lib.pn_grid_mlp_bwd(C.byref(ps), C.byref(m), C.byref(ga), _byref(gb), nb, mb, apply_mask,
                                                 C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
                                                 C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_grid_mlp_bwd")
+                if GRAD_READY_HOOK is not None and gg is not None:
+                    GRAD_READY_HOOK(p.grid_a, gg)          # this grid's gradient is final (one pass writes each grid)
                 if want_w[i]:
                     gp = zeros_like_flat(p.params)
                     g = L.PnGridMlpGrad()
@@ -338,6 +340,8 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                     with L.timed(f"grid_mlp_wgrad:{p.dec.name}", device):
                         L.check(lib.pn_grid_mlp_wgrad(C.c_int64(n), C.byref(m), C.byref(sst), C.byref(wst), C.byref(g), st),
                                 "pn_grid_mlp_wgrad")
+                    if GRAD_READY_HOOK is not None:
+                        GRAD_READY_HOOK(("params", p.dec.name), gp)
                     g_params.append(gp)
                 else:
                     g_params.append(None)
@@ -359,6 +363,14 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                 else:
                     g_params.append(None)
     return g_grids, g_pts, g_params
+
+
+# Optional callback ``hook(key, grad)`` fired from inside the backward as soon as a gradient
+# buffer is complete: key = grid name with the (1,32,Z,Y,X) channels-last gradient, or
+# ("params", decoder name) with the list of that decoder's parameter gradients (views of one
+# flat buffer).  dist.OverlappedGradReducer uses it to start the NCCL all-reduce of a finished
+# gradient while the remaining decoder kernels still run.
+GRAD_READY_HOOK = None
 
 
 def zeros_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:

@@ -69,3 +69,47 @@ def test_shard_bounds_cover_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _reducer_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from pointnerf_slam_b200 import dist as D
+    from pointnerf_slam_b200 import engine as E
+    import pointnerf_slam_b200 as P
+    D.init_from_env("gloo")
+    torch.manual_seed(rank)
+    # a grid leaf whose .grad autograd COPIED, and a decoder whose .grad are the hook's own views
+    leaf = torch.zeros(1, 32, 3, 4, 5).contiguous(memory_format=torch.channels_last_3d)
+    g = torch.randn(1, 3, 4, 5, 32).permute(0, 4, 1, 2, 3)       # channels-last gradient buffer
+    leaf.grad = g.clone()
+    dec = P.NICE(coarse=False).color_decoder
+    params = E.grid_mlp_tensors(dec)
+    gp = E.zeros_like_flat(params)
+    for t in gp:
+        t.copy_(torch.randn(t.shape))
+    for p_, t in zip(params, gp):
+        p_.grad = t
+    pose = torch.randn(7)
+    expect_grid, expect_p0, expect_pose = g.clone(), gp[1].clone(), pose.clone()
+    red = D.OverlappedGradReducer()
+    with red:
+        assert E.GRAD_READY_HOOK is not None
+        E.GRAD_READY_HOOK("grid_color", g)
+        E.GRAD_READY_HOOK(("params", "color"), gp)
+    assert E.GRAD_READY_HOOK is None
+    red.finish({"grid_color": leaf}, decoders={"color": dec}, others=[pose])
+    for t in (expect_grid, expect_p0, expect_pose):
+        dist.all_reduce(t)
+    ok = torch.allclose(leaf.grad, expect_grid) and torch.allclose(params[1].grad, expect_p0) and torch.allclose(pose, expect_pose)
+    if rank == 0:
+        torch.save({"ok": bool(ok)}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_reducer_two_ranks(tmp_path):
+    out = str(tmp_path / "r.pt")
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_reducer_worker, args=(2, port, out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]
