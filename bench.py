@@ -150,7 +150,14 @@ def run_ours(args):
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    reducer = D.OverlappedGradReducer()
+    # N > 1: every gradient sink of the backward comes from one arena -> one memset, one all-reduce
+    from pointnerf_slam_b200 import engine as E
+    arena = None
+    if world > 1:
+        n_arena = sum(g.numel() for k, g in grids.items() if k != "grid_coarse") + 65536
+        arena = E.GradArena(n_arena, dev)
+        E.GRAD_ARENA = arena
+    reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "arena") == "arena" else None)
 
     def step(e2e=False):
         if e2e:  # host -> device copy of this step's inputs from pinned memory
@@ -171,7 +178,11 @@ def run_ours(args):
         # Mapper.py:641-646 (masked L1 depth + weighted L1 colour), written without boolean indexing so that
         # the host does not synchronise in the middle of the step
         loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
-        if world > 1:   # all-reduce each gradient as soon as the backward has produced it
+        if world > 1 and os.environ.get("PN_BENCH_ALLREDUCE", "arena") == "simple":
+            loss.backward()
+            D.allreduce_gradients([t.grad for t in trained])
+        elif world > 1:   # one all-reduce over the gradient arena (or per-gradient overlapped reductions)
+            arena.reset()
             with reducer:
                 loss.backward()
             reducer.finish({k: grids[k] for k in ("grid_middle", "grid_fine", "grid_color")},

@@ -119,8 +119,11 @@ class OverlappedGradReducer:
                    others=[cam.grad for cam in cams])
     """
 
-    def __init__(self):
+    def __init__(self, arena=None):
+        """With ``arena`` (an engine.GradArena that the backward allocates from) the hook only
+        records the buffers and ``finish`` issues ONE all-reduce over the used part of the arena."""
         self.items = []    # (key, tensor or list, flat buffer reduced, work)
+        self.arena = arena
 
     def __enter__(self):
         from . import engine
@@ -135,6 +138,11 @@ class OverlappedGradReducer:
 
     def _ready(self, key, grad):
         if world_size() == 1:
+            return
+        if self.arena is not None:
+            first = grad[0] if isinstance(grad, (list, tuple)) else grad
+            in_arena = self.arena.owns(first)
+            self.items.append((key, list(grad) if isinstance(grad, (list, tuple)) else grad, "arena" if in_arena else None, None))
             return
         if isinstance(grad, (list, tuple)):           # parameter gradients: views of one flat buffer
             flat = grad[0]._base if grad[0]._base is not None else None
@@ -158,9 +166,13 @@ class OverlappedGradReducer:
         ``decoders``: decoder name -> module whose parameters were trained; ``others``: extra
         gradient tensors (poses ...) reduced here in one bucket."""
         late = []
+        if self.arena is not None and world_size() > 1 and self.arena.offset:
+            dist.all_reduce(self.arena.used(), op=dist.ReduceOp.SUM)
         for key, grad, buf, work in self.items:
             if work is not None:
                 work.wait()
+            elif buf == "arena":
+                work = True                            # reduced by the arena all-reduce above
             if isinstance(grad, list):
                 dec = (decoders or {}).get(key[1])
                 leaves = None

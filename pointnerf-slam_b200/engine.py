@@ -169,10 +169,55 @@ def grid_channels_last(g: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class GradArena:
+    """One flat float32 buffer that the backward carves its grid and parameter gradient
+    sinks from (in a fixed order every iteration).  One memset zeroes them all and -- on
+    several GPUs -- ONE all-reduce over ``used()`` sums every gradient of the iteration
+    (launch latency, not link count, sizes the exchange).  Install with
+    ``engine.GRAD_ARENA = arena`` and call ``arena.reset()`` before each backward."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros(int(numel), dtype=torch.float32, device=device)
+        self.offset = 0
+
+    def reset(self) -> None:
+        if self.offset:
+            self.buf[:self.offset].zero_()
+        self.offset = 0
+
+    def take(self, numel: int) -> Optional[torch.Tensor]:
+        n = (int(numel) + 31) // 32 * 32          # keep every sink 128-byte aligned
+        if self.offset + n > self.buf.numel():
+            return None                            # arena too small: caller falls back to a fresh buffer
+        v = self.buf[self.offset:self.offset + int(numel)]
+        self.offset += n
+        return v
+
+    def used(self) -> torch.Tensor:
+        return self.buf[:self.offset]
+
+    def owns(self, t: Optional[torch.Tensor]) -> bool:
+        if t is None:
+            return False
+        lo = self.buf.data_ptr()
+        return lo <= t.data_ptr() < lo + self.buf.numel() * 4
+
+
+GRAD_ARENA: Optional[GradArena] = None
+
+
+def _zeros(numel: int, device) -> torch.Tensor:
+    if GRAD_ARENA is not None and GRAD_ARENA.buf.device == torch.device(device):
+        v = GRAD_ARENA.take(numel)
+        if v is not None:
+            return v                               # zeroed by GradArena.reset()
+    return torch.zeros(int(numel), dtype=torch.float32, device=device)
+
+
 def new_grid_grad(g: torch.Tensor) -> torch.Tensor:
     """Zeroed gradient buffer shaped like g with channels-last memory."""
-    return torch.zeros((1, g.shape[2], g.shape[3], g.shape[4], 32), device=g.device,
-                       dtype=torch.float32).permute(0, 4, 1, 2, 3)
+    n = g.shape[2] * g.shape[3] * g.shape[4] * 32
+    return _zeros(n, g.device).view(1, g.shape[2], g.shape[3], g.shape[4], 32).permute(0, 4, 1, 2, 3)
 
 
 def _pn_grid(g: Optional[torch.Tensor]) -> Optional[L.PnGrid]:
@@ -377,7 +422,7 @@ def zeros_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     """Zeroed gradient sinks for a list of parameters, carved out of ONE buffer (one
     memset launch instead of one per parameter; every view stays 16-byte aligned)."""
     sizes = [(t.numel() + 3) // 4 * 4 for t in tensors]
-    flat = torch.zeros(sum(sizes), dtype=tensors[0].dtype, device=tensors[0].device)
+    flat = _zeros(sum(sizes), tensors[0].device)
     out, off = [], 0
     for t, sz in zip(tensors, sizes):
         out.append(flat[off:off + t.numel()].view(t.shape))

@@ -102,6 +102,28 @@ def _reducer_worker(rank, world, port, out):
     for t in (expect_grid, expect_p0, expect_pose):
         dist.all_reduce(t)
     ok = torch.allclose(leaf.grad, expect_grid) and torch.allclose(params[1].grad, expect_p0) and torch.allclose(pose, expect_pose)
+    # arena mode: sinks carved from one buffer, ONE all-reduce in finish()
+    arena = E.GradArena(1 << 16, "cpu")
+    E.GRAD_ARENA = arena
+    arena.reset()
+    g2 = E.new_grid_grad(leaf)
+    g2.copy_(torch.randn(g2.shape))
+    gp2 = E.zeros_like_flat(params)
+    for t in gp2:
+        t.copy_(torch.randn(t.shape))
+    assert arena.owns(g2) and arena.owns(gp2[3])
+    leaf.grad = g2                       # autograd kept the buffer itself
+    for p_, t in zip(params, gp2):
+        p_.grad = t.clone()              # autograd copied
+    e_grid, e_p3 = g2.clone(), gp2[3].clone()
+    red2 = D.OverlappedGradReducer(arena)
+    with red2:
+        E.GRAD_READY_HOOK("grid_color", g2)
+        E.GRAD_READY_HOOK(("params", "color"), gp2)
+    red2.finish({"grid_color": leaf}, decoders={"color": dec})
+    E.GRAD_ARENA = None
+    dist.all_reduce(e_grid); dist.all_reduce(e_p3)
+    ok = ok and torch.allclose(leaf.grad, e_grid) and torch.allclose(params[3].grad, e_p3)
     if rank == 0:
         torch.save({"ok": bool(ok)}, out)
     dist.barrier()
