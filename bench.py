@@ -159,11 +159,13 @@ def run_ours(args):
         E.GRAD_ARENA = arena
     reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "arena") == "arena" else None)
 
-    def step(e2e=False):
-        if e2e:  # host -> device copy of this step's inputs from pinned memory
-            frames[0][0].copy_(pinned_depth, non_blocking=True)
-            frames[0][1].copy_(pinned_color, non_blocking=True)
-            poses_dev.copy_(pinned_poses, non_blocking=True)
+    def h2d_inputs():   # host -> device copy of this step's inputs from pinned memory (e2e only)
+        frames[0][0].copy_(pinned_depth, non_blocking=True)
+        frames[0][1].copy_(pinned_color, non_blocking=True)
+        poses_dev.copy_(pinned_poses, non_blocking=True)
+
+    def step_body():
+        """One mapping iteration through the public API: sampling, render, loss, backward (+ gradient exchange)."""
         ro, rd, gd, gc = [], [], [], []
         for k in range(N_KEYFRAMES):
             c2w = P.get_camera_from_tensor(cams[k])
@@ -189,10 +191,44 @@ def run_ours(args):
                            decoders={"color": model.color_decoder}, others=[c.grad for c in cams[1:]])
         else:
             loss.backward()
+        return loss
+
+    def eager_step(e2e=False):
+        if e2e:
+            h2d_inputs()
+        loss = step_body()
         out = loss.item() if e2e else None  # device -> host read of the step's result
         for t in trained:
             t.grad = None
         return out
+
+    # The iteration is launch-bound on the host (~45 kernel launches + autograd), so it is captured ONCE
+    # into a CUDA graph -- the very same API calls, kernels and collectives -- and replayed per step.
+    graph = {"g": None, "loss": None, "launches": 0}
+
+    def capture():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                eager_step(False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(gen)
+        n0 = L.lib().pn_launch_count()
+        with torch.cuda.graph(g):
+            graph["loss"] = step_body()
+        graph["launches"] = L.lib().pn_launch_count() - n0
+        graph["g"] = g
+
+    def step(e2e=False):
+        if graph["g"] is None:
+            return eager_step(e2e)
+        if e2e:
+            h2d_inputs()
+        graph["g"].replay()
+        return graph["loss"].item() if e2e else None
 
     def timed(k, e2e, profile):
         L.PROFILE = {} if profile else None
@@ -206,7 +242,7 @@ def run_ours(args):
             flush.fill_(1)      # evict L2 between timed iterations (not timed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            step(e2e)
+            (eager_step if profile else step)(e2e)
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -219,14 +255,31 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         prof = L.PROFILE
         L.PROFILE = None
-        return t.item(), L.lib().pn_launch_count() - n0, prof, wall
+        launched = L.lib().pn_launch_count() - n0
+        if graph["g"] is not None and not profile:
+            launched = graph["launches"] * k
+        return t.item(), launched, prof, wall
 
     for _ in range(max(args.warmup, 3)):
+        eager_step(False)
+    # per-kernel durations (CUDA events around every C-ABI call) come from an eager pass over the same K steps;
+    # the headline is timed on graph replays (events cannot be read back from inside a captured graph)
+    ms_eager, launches_eager, prof, _ = timed(args.steps, False, True)
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            capture()
+        except Exception as exc:   # a capture problem must not lose the measurement: fall back to eager launches
+            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); timing eager launches", file=sys.stderr)
+            graph["g"] = None
+            use_graph = False
+            torch.cuda.synchronize()
+    for _ in range(3):
         step(False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, launches, prof, _ = timed(args.steps, False, True)
+    ms_total, launches, _, _ = timed(args.steps, False, False)
     clocks = sampler.stop() if rank == 0 else None
     if args.light:
         ms_e2e = ms_total
@@ -241,7 +294,7 @@ def run_ours(args):
     hbm, which = peaks()
     # dominant kernel: largest total event time among the profiled C-ABI calls
     kern = {k: [a.elapsed_time(b) for a, b in v] for k, v in (prof or {}).items()}
-    share = {k: sum(v) / ms_total for k, v in kern.items()}
+    share = {k: sum(v) / ms_eager for k, v in kern.items()}
     top = max(kern, key=lambda k: sum(kern[k])) if kern else None
     n_samples = N_KEYFRAMES * PIX_PER_KF * S
     # algorithmic bytes per launch of each decoder kernel (DESIGN.md "roofline"): gathers of 1024 B
@@ -281,7 +334,9 @@ def run_ours(args):
                        "(max error 5e-7 relative, tests/test_gpu_tc.py); float64 geometry as in the reference",
                        "rays_per_step_per_gpu": N_KEYFRAMES * PIX_PER_KF, "samples_per_ray": S,
                        "grids": {k: list(v.shape) for k, v in grids.items()}, "l2": "flushed between timed iterations "
-                       "(256 MiB fill, untimed); per-step CUDA events summed", "parallelism": f"ray-shard dp{world}"},
+                       "(256 MiB fill, untimed); per-step CUDA events summed", "parallelism": f"ray-shard dp{world}",
+                       "launch": ("whole iteration captured once in a CUDA graph and replayed" if use_graph else "eager launches"),
+                       "eager_ms_per_step": round(ms_eager / args.steps, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s",
                     "h2d_bytes_per_step": pinned_depth.numel() * 4 + pinned_color.numel() * 4 + pinned_poses.numel() * 4,
                     "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 4)},
@@ -292,8 +347,24 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline(sample_kf_pixels=200, iters=2)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    # Teardown.  A captured graph that contains NCCL kernels must be released before the process group
+    # goes away, and no rank may sit in a collective at exit: drop the graph, synchronise, and leave
+    # through os._exit (skipping NCCL's destructor-time rendezvous, which can wait forever on a
+    # communicator that still has captured work).
+    watchdog = threading.Timer(60.0, lambda: os._exit(0))   # never outlive the measurement by more than a minute
+    watchdog.daemon = True
+    watchdog.start()
+    graph["g"] = None
+    graph["loss"] = None
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------
@@ -382,6 +453,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--light", action="store_true", help="profiling runs: skip the e2e pass and the CPU baseline")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
