@@ -534,53 +534,75 @@ __global__ void __launch_bounds__(kThreads, 2) k_wgrad_gemm(const WgArgs a) {
 }
 
 // dWo[o][k] += sum_n GO[n][o] H4[n][k],  dbo[o] += sum_n GO[n][o]
+// warp = feature quad of h_4 (8 quads), lane = sample slot: every load is a coalesced 512-byte row of the
+// planar-4 stash; 16 + 4 partial sums per thread, reduced over the 32 sample lanes by shuffles at the end.
 __global__ void __launch_bounds__(kThreads) k_wgrad_out(const float* __restrict__ GO, const float* __restrict__ H4, int64_t N,
                                                        int nout, float* __restrict__ dWo, float* __restrict__ dbo) {
-  __shared__ float red[8][4][33];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t n = (int64_t)blockIdx.x * 8 + warp; n < N; n += (int64_t)gridDim.x * 8) {
-    const float4 g = reinterpret_cast<const float4*>(GO)[n];
-    const float h = H4[((int64_t)(lane >> 2) * N + n) * 4 + (lane & 3)];
-    acc[0] = fmaf(g.x, h, acc[0]); acc[1] = fmaf(g.y, h, acc[1]); acc[2] = fmaf(g.z, h, acc[2]); acc[3] = fmaf(g.w, h, acc[3]);
-    bs[0] += g.x; bs[1] += g.y; bs[2] += g.z; bs[3] += g.w;
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  float acc[4][4];
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[o][i] = 0.f;
+  const float4* H = reinterpret_cast<const float4*>(H4) + (int64_t)q * N;
+  const float4* G = reinterpret_cast<const float4*>(GO);
+#pragma unroll 4
+  for (int64_t n = (int64_t)blockIdx.x * 32 + lane; n < N; n += (int64_t)gridDim.x * 32) {
+    const float4 h = H[n], g = G[n];
+    const float gv[4] = {g.x, g.y, g.z, g.w}, hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      bs[o] += gv[o];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[o][i] = fmaf(gv[o], hv[i], acc[o][i]);
+    }
   }
 #pragma unroll
-  for (int o = 0; o < 4; ++o) { red[warp][o][lane] = acc[o]; if (lane == 0) red[warp][o][32] = bs[o]; }
-  __syncthreads();
-  if (tid < 4 * 33) {
-    const int o = tid / 33, k = tid % 33;
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][o][k];
+  for (int o = 0; o < 4; ++o) {
     if (o < nout) {
-      if (k < 32) { if (dWo) atomicAdd(dWo + o * 32 + k, s); }
-      else if (dbo) atomicAdd(dbo + o, s);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v = warp_sum(acc[o][i]);
+        if (lane == 0 && dWo) atomicAdd(dWo + o * 32 + 4 * q + i, v);
+      }
+      if (q == 0) {
+        const float v = warp_sum(bs[o]);
+        if (lane == 0 && dbo) atomicAdd(dbo + o, v);
+      }
     }
   }
 }
 
 // dB[d][k] += sum_n P32[d][n] GARG[n][k]
-__global__ void __launch_bounds__(kThreads) k_wgrad_B(const float* __restrict__ P32, const float* __restrict__ GARG, int64_t N,
-                                                     float* __restrict__ dB) {
-  __shared__ float red[8][3][32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk = blockIdx.y;  // 32 embedding columns per chunk
-  const int k = chunk * 32 + lane;
-  float acc[3] = {0.f, 0.f, 0.f};
-  for (int64_t n = (int64_t)blockIdx.x * 8 + warp; n < N; n += (int64_t)gridDim.x * 8) {
-    const float g = GARG[((int64_t)(k >> 2) * N + n) * 4 + (k & 3)];
-    acc[0] = fmaf(P32[n], g, acc[0]); acc[1] = fmaf(P32[N + n], g, acc[1]); acc[2] = fmaf(P32[2 * N + n], g, acc[2]);
+// warp = embedding quad (24 quads, 768 threads), lane = sample slot; coalesced rows, 12 partial sums per thread.
+__global__ void __launch_bounds__(768) k_wgrad_B(const float* __restrict__ P32, const float* __restrict__ GARG, int64_t N,
+                                                float* __restrict__ dB) {
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  float acc[3][4];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[d][i] = 0.f;
+  const float4* G = reinterpret_cast<const float4*>(GARG) + (int64_t)q * N;
+#pragma unroll 4
+  for (int64_t n = (int64_t)blockIdx.x * 32 + lane; n < N; n += (int64_t)gridDim.x * 32) {
+    const float4 g = G[n];
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    const float p[3] = {P32[n], P32[N + n], P32[2 * N + n]};
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[d][i] = fmaf(p[d], gv[i], acc[d][i]);
   }
 #pragma unroll
-  for (int d = 0; d < 3; ++d) red[warp][d][lane] = acc[d];
-  __syncthreads();
-  if (tid < 96) {
-    const int d = tid >> 5, l = tid & 31;
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][d][l];
-    const int kk = chunk * 32 + l;
-    if (kk < PN_EMBED) atomicAdd(dB + d * PN_EMBED + kk, s);
-  }
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float v = warp_sum(acc[d][i]);
+      const int k = 4 * q + i;
+      if (lane == 0 && k < PN_EMBED) atomicAdd(dB + d * PN_EMBED + k, v);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1555,13 +1577,13 @@ extern "C" int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash
     if (launch_status("k_wgrad_gemm")) return 1;
   }
   if (g->Wo || g->bo) {
-    int grid = (int)((N + 7) / 8); if (grid > 2 * sm_count()) grid = 2 * sm_count();
+    int grid = (int)((N + 31) / 32); if (grid > 2 * sm_count()) grid = 2 * sm_count();
     k_wgrad_out<<<grid, kThreads, 0, st>>>(ws->GO, stash->H + 4 * blk, N, w->n_out, g->Wo, g->bo);
     if (launch_status("k_wgrad_out")) return 1;
   }
   if (g->B) {
-    int grid = (int)((N + 7) / 8); if (grid > sm_count()) grid = sm_count();
-    k_wgrad_B<<<dim3(grid, 3), kThreads, 0, st>>>(ws->P32, ws->GARG, N, g->B);
+    int grid = (int)((N + 31) / 32); if (grid > 2 * sm_count()) grid = 2 * sm_count();
+    k_wgrad_B<<<grid, 768, 0, st>>>(ws->P32, ws->GARG, N, g->B);
     if (launch_status("k_wgrad_B")) return 1;
   }
   return 0;
@@ -1661,7 +1683,7 @@ extern "C" int pn_coarse_mlp_wgrad(int64_t N, const pn_stash* stash, const pn_ws
     if (launch_status("k_wgrad_gemm")) return 1;
   }
   if (g->Wo || g->bo) {
-    int grid = (int)((N + 7) / 8); if (grid > 2 * sm_count()) grid = 2 * sm_count();
+    int grid = (int)((N + 31) / 32); if (grid > 2 * sm_count()) grid = 2 * sm_count();
     k_wgrad_out<<<grid, kThreads, 0, st>>>(ws->GO, stash->H + 4 * blk, N, 1, g->Wo, g->bo);
     if (launch_status("k_wgrad_out")) return 1;
   }
