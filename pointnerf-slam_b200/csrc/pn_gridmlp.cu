@@ -608,31 +608,32 @@ __global__ void __launch_bounds__(768) k_wgrad_B(const float* __restrict__ P32, 
 // ---------------------------------------------------------------------------
 // forward on the 5th-gen tensor cores (tcgen05, kind::tf32, 3xTF32 split)
 // ---------------------------------------------------------------------------
-// CTA = 256 threads = two independent groups of 128; a group owns one tile of 128 consecutive
-// samples at a time (thread = sample row = TMEM lane).  Per tile every decoder layer is a
-// D[128 x 32] (+)= A[128 x K] . W[32 x K]^T tensor-core product: the activation operand A is
-// written by the group (hi and lo copies, canonical K-major layout) into its 32 KB shared
-// buffer, the weights sit pre-split in shared memory for the whole kernel, the accumulators
+// CTA = 512 threads = two independent groups of 256; a group owns one tile of 128 consecutive
+// samples at a time (two threads per sample row = TMEM lane, 16 columns each).  Per tile every
+// decoder layer is a D[128 x N] (+)= A[128 x 32] . W[N x 32]^T tensor-core product: the activation
+// operand A is written by the group (hi and lo copies, canonical K-major layout) into its 32 KB
+// shared buffer, the weights sit pre-split in shared memory for the whole kernel, the accumulators
 // live in the group's 256 tensor-memory columns:
-//     cols   0..159  D2_l = Wc_l . c           (feature term of block l, issued up front)
-//     cols 160..191  D1_0 = W0 . emb           (3 K-chunks of 32)
+//     cols   0..159  D2_l = Wc_l . c           (feature terms of all five blocks: ONE N=160 product)
+//     cols 160..191  D1_0 = W0 . emb           (3 K-chunks of 32; D1_0 and D1_3 are ONE N=64 product)
 //     cols 192..223  D1_3 = W3[:, :93] . emb + W3[:, 93:] . h2
 //     cols 224..255  D1_x = W_l . h_{l-1}      (blocks 1, 2, 4)
 // The epilogue of a block reads its accumulators back (tcgen05.ld), applies
-// relu(D1 + b) + D2 + bc in registers, records the ReLU bits / stash, re-splits into hi/lo
-// and stores the next A operand.  While one group waits for its MMAs the other group runs.
+// relu(D1 + b) + D2 + bc in registers, re-splits into hi/lo and stores the next A operand.
+// Everything that does not depend on the product in flight -- the next chunk's sines, the second
+// grid's gather, the stash stores, the next block's D2 + bc -- is done between issuing the MMAs
+// and waiting for them; while one group waits the other group runs.
 namespace tc {
 constexpr uint32_t kLbo = 128;                       // core matrices adjacent in K
 constexpr uint32_t kASbo = 8 * 128;                  // A buffer: K = 32 per 8-row group
 constexpr uint32_t kABytes = 16 * kASbo;             // one 128 x 32 operand copy (16 KB)
 __host__ __device__ constexpr uint32_t bsbo(int K) { return (uint32_t)(K / 4) * 128u; }
 __host__ __device__ constexpr uint32_t bbytes(int K) { return 4u * bsbo(K); }  // 32 rows
-// byte offsets of the pre-split weight operands (hi copy; lo copy follows at +bbytes)
-constexpr uint32_t O_W0 = 0;
-constexpr uint32_t O_W3E = O_W0 + 2 * bbytes(96);
-constexpr uint32_t O_WH = O_W3E + 2 * bbytes(96);    // 4 x [32 x 32]
-constexpr uint32_t O_WC = O_WH + 4 * 2 * bbytes(32);
-template <int CD> __host__ __device__ constexpr uint32_t o_a() { return O_WC + 5u * 2u * bbytes(CD); }   // A buffers
+// byte offsets of the pre-split weight operands
+constexpr uint32_t O_WE = 0;                         // [W0; W3[:, :93]] as one [64 x 96] operand: hi, then lo
+constexpr uint32_t O_WH = O_WE + 4 * bbytes(96);     // 4 x [32 x 32]: hi, lo per block
+template <int CD> __host__ __device__ constexpr uint32_t o_wc() { return O_WH + 4 * 2 * bbytes(32); }   // [160 x CD]: hi, then lo
+template <int CD> __host__ __device__ constexpr uint32_t o_a() { return o_wc<CD>() + 5u * 2u * bbytes(CD); }   // A buffers
 template <int CD> __host__ __device__ constexpr uint32_t o_small() { return o_a<CD>() + 2u * 2u * kABytes; }
 constexpr int S_B = 0, S_BIAS = 288, S_BC = 448, S_WO = 608, S_BO = 736, S_TOTAL = 740;  // floats
 // the two mbarriers and the TMEM base address follow the float area (kept in dynamic shared
@@ -641,8 +642,8 @@ template <int CD> __host__ __device__ constexpr uint32_t smem_total() { return o
 
 // split a [32 x K] row-major weight block (row stride ld, starting column col0, `kvalid` real
 // columns, zero beyond) into canonical hi / lo operands
-__device__ __forceinline__ void stage_b(unsigned char* hi, const float* __restrict__ src, int ld, int col0, int K, int kvalid) {
-  unsigned char* lo = hi + bbytes(K);
+__device__ __forceinline__ void stage_b(unsigned char* hi, unsigned char* lo, const float* __restrict__ src, int ld, int col0, int K,
+                                        int kvalid) {
   for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
     const int n = i / K, k = i - n * K;
     const float w = k < kvalid ? src[n * ld + col0 + k] : 0.f;
@@ -653,60 +654,12 @@ __device__ __forceinline__ void stage_b(unsigned char* hi, const float* __restri
     *reinterpret_cast<float*>(lo + off) = l;
   }
 }
-
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
-
-// write this thread's 32-wide row (hi and lo) into the group's A buffer
-__device__ __forceinline__ void store_row(unsigned char* a_hi, int row, const float (&v)[32]) {
-  unsigned char* a_lo = a_hi + kABytes;
-  const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float4 h, l;
-    umma::split_tf32(v[4 * q], h.x, l.x); umma::split_tf32(v[4 * q + 1], h.y, l.y);
-    umma::split_tf32(v[4 * q + 2], h.z, l.z); umma::split_tf32(v[4 * q + 3], h.w, l.w);
-    *reinterpret_cast<float4*>(a_hi + base + q * kLbo) = h;
-    *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
-  }
-}
-
-// Trilinear features of the group's 128 rows straight into the A operand.  8 lanes per
-// sample (lane&7 = channel quad, 128-bit loads), 4 samples per warp iteration.
-__device__ __forceinline__ void gather_rows(const GridDev& g, float ux, float uy, float uz, unsigned valid_mask, int lane,
-                                            int warp_row0, unsigned char* a_hi, float* __restrict__ Cst, int64_t N, int64_t n0) {
-  unsigned char* a_lo = a_hi + kABytes;
-  const int q = lane & 7, sub = lane >> 3;
-#pragma unroll 4
-  for (int it = 0; it < 8; ++it) {
-    const int src = 4 * it + sub;
-    const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((valid_mask >> src) & 1u) {
-      const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
-      const float4* gp = reinterpret_cast<const float4*>(g.data + c.base) + q;
-      float4 val[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        val[k] = ((c.ok >> k) & 1u) ? __ldg(gp + corner_offset(k, g.W, g.H) / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if ((c.ok >> k) & 1u) {
-          const float w = corner_weight(c, k);
-          v.x = __fadd_rn(v.x, __fmul_rn(val[k].x, w)); v.y = __fadd_rn(v.y, __fmul_rn(val[k].y, w));
-          v.z = __fadd_rn(v.z, __fmul_rn(val[k].z, w)); v.w = __fadd_rn(v.w, __fmul_rn(val[k].w, w));
-        }
-      }
-      if (Cst) reinterpret_cast<float4*>(Cst)[(int64_t)q * N + n0 + src] = v;
-    }
-    const int row = warp_row0 + src;
-    float4 h, l;
-    umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y); umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
-    const uint32_t off = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)q * kLbo;
-    *reinterpret_cast<float4*>(a_hi + off) = h;
-    *reinterpret_cast<float4*>(a_lo + off) = l;
-  }
-}
 }  // namespace tc
+
+// 128-bit vector reduction into global memory (sm_90+): four float atomics in one instruction
+__device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 
 // TMEM -> registers, 16 columns
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -741,13 +694,15 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   // ---- one-time set-up: TMEM, barriers, weights
   if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
-  stage_b(smraw + O_W0, a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
-  stage_b(smraw + O_W3E, a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
-  stage_b(smraw + O_WH, a.w.W[1], 32, 0, 32, 32);
-  stage_b(smraw + O_WH + 2 * bbytes(32), a.w.W[2], 32, 0, 32, 32);
-  stage_b(smraw + O_WH + 4 * bbytes(32), a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
-  stage_b(smraw + O_WH + 6 * bbytes(32), a.w.W[4], 32, 0, 32, 32);
-  for (int l = 0; l < 5; ++l) stage_b(smraw + O_WC + (uint32_t)l * 2u * bbytes(CD), a.w.Wc[l], CD, 0, CD, CD);
+  constexpr uint32_t O_WC = o_wc<CD>();
+  stage_b(smraw + O_WE, smraw + O_WE + 2 * bbytes(96), a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
+  stage_b(smraw + O_WE + bbytes(96), smraw + O_WE + 3 * bbytes(96), a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
+  stage_b(smraw + O_WH, smraw + O_WH + bbytes(32), a.w.W[1], 32, 0, 32, 32);
+  stage_b(smraw + O_WH + 2 * bbytes(32), smraw + O_WH + 3 * bbytes(32), a.w.W[2], 32, 0, 32, 32);
+  stage_b(smraw + O_WH + 4 * bbytes(32), smraw + O_WH + 5 * bbytes(32), a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
+  stage_b(smraw + O_WH + 6 * bbytes(32), smraw + O_WH + 7 * bbytes(32), a.w.W[4], 32, 0, 32, 32);
+  for (int l = 0; l < 5; ++l)
+    stage_b(smraw + O_WC + (uint32_t)l * bbytes(CD), smraw + O_WC + (uint32_t)(5 + l) * bbytes(CD), a.w.Wc[l], CD, 0, CD, CD);
   for (int i = tid; i < 288; i += 512) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
   for (int i = tid; i < 160; i += 512) { sm[S_BIAS + i] = a.w.b[i >> 5][i & 31]; sm[S_BC + i] = a.w.bc[i >> 5][i & 31]; }
   for (int i = tid; i < 128; i += 512) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
@@ -760,24 +715,29 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);        // this warp's lanes
   const uint32_t sA = umma::smem_u32(a_hi), sAlo = sA + kABytes;
   const uint32_t sW = umma::smem_u32(smraw);
-  constexpr uint32_t idesc = umma::instr_desc_tf32(128, 32);
+  constexpr uint32_t idesc32 = umma::instr_desc_tf32(128, 32), idesc64 = umma::instr_desc_tf32(128, 64),
+                     idesc160 = umma::instr_desc_tf32(128, 160);
   uint64_t* bar = &bars[grp];
   uint32_t phase = 0;
   const bool issuer = (tid & 255) == 0;
   const uint64_t dA_hi = umma::smem_desc(sA, kLbo, kASbo), dA_lo = umma::smem_desc(sAlo, kLbo, kASbo);
   constexpr uint32_t kStep = (2u * kLbo) >> 4;   // one K-step of 8 in descriptor address units
-  // D(+)= A . B[:, 32*k32 .. 32*k32+31] of the [32 x Kb] operand at byte offset boff
-  auto mma = [&](uint32_t dcol, uint32_t boff, int Kb, int k32, uint32_t acc) {
+  // D[:, dcol .. dcol+N) (+)= A . B[:, 32*k32 .. 32*k32+31]^T for the [N x Kb] operand whose hi copy
+  // starts at byte offset boff and whose lo copy follows lo_off bytes later
+  auto mma = [&](uint32_t dcol, uint32_t boff, uint32_t lo_off, int Kb, int k32, uint32_t idesc, uint32_t acc) {
     const uint32_t bh = sW + boff + (uint32_t)k32 * 8u * kLbo;
-    const uint64_t dB_hi = umma::smem_desc(bh, kLbo, bsbo(Kb)), dB_lo = umma::smem_desc(bh + bbytes(Kb), kLbo, bsbo(Kb));
+    const uint64_t dB_hi = umma::smem_desc(bh, kLbo, bsbo(Kb)), dB_lo = umma::smem_desc(bh + lo_off, kLbo, bsbo(Kb));
     umma::mma_3xtf32_k32(tm + dcol, dA_hi, dA_lo, dB_hi, dB_lo, kStep, kStep, idesc, acc);
   };
-  auto publish_and_issue = [&](auto&& issue) {   // A written -> MMAs -> wait for completion
+  // A written by every thread of the group -> one thread issues the MMAs and commits them to the barrier
+  auto publish_issue = [&](auto&& issue) {
     umma::fence_proxy_async();
     umma::tc_fence_before();
     asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
     if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
-    // one lane polls the mbarrier; the other 255 threads of the group sleep on a named barrier
+  };
+  // one lane polls the mbarrier; the other 255 threads of the group sleep on a named barrier
+  auto wait_mma = [&] {
     if ((tid & 255) < 32) { if (lane == 0) umma::mbar_wait(bar, phase); __syncwarp(); }
     asm volatile("bar.sync %0, 256;" ::"r"(grp + 4) : "memory");
     phase ^= 1u;
@@ -795,10 +755,12 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
       *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
     }
   };
-  // trilinear features of rows 32*quarter + 16*half + [0,16) -> A operand; 8 lanes per sample
-  auto gather16 = [&](const GridDev& g, float ux, float uy, float uz, unsigned vm, float* __restrict__ Cst, int64_t N, int64_t nq) {
+  // trilinear features of rows 32*quarter + 16*half + [0,16): 8 lanes per sample (lane&7 = channel quad,
+  // 128-bit loads), 4 samples per iteration; the values stay in registers until put_rows
+  auto gather16 = [&](const GridDev& g, float ux, float uy, float uz, unsigned vm, float* __restrict__ Cst, int64_t N, int64_t nq,
+                      float4 (&out)[4]) {
     const int q = lane & 7, sub = lane >> 3;
-#pragma unroll 2
+#pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int src = 16 * half + 4 * it + sub;   // lane (within this warp) that owns the row
       const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
@@ -820,9 +782,17 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
         }
         if (Cst) reinterpret_cast<float4*>(Cst)[(int64_t)q * N + nq + src] = v;
       }
-      const int r = quarter * 32 + src;
+      out[it] = v;
+    }
+  };
+  auto put_rows = [&](const float4 (&v)[4]) {
+    const int q = lane & 7, sub = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = quarter * 32 + 16 * half + 4 * it + sub;
       float4 h, l;
-      umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y); umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+      umma::split_tf32(v[it].x, h.x, l.x); umma::split_tf32(v[it].y, h.y, l.y);
+      umma::split_tf32(v[it].z, h.z, l.z); umma::split_tf32(v[it].w, h.w, l.w);
       const uint32_t off = (uint32_t)(r >> 3) * kASbo + (uint32_t)(r & 7) * 16u + (uint32_t)q * kLbo;
       *reinterpret_cast<float4*>(a_hi + off) = h;
       *reinterpret_cast<float4*>(a_lo + off) = l;
@@ -839,18 +809,21 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
     const unsigned vm = __ballot_sync(kFull, valid);
     const int64_t nq = t * 128 + quarter * 32;
     // ---- feature terms of all five blocks
-    gather16(a.ga, unnormalise(sp.xn[0], a.ga.W), unnormalise(sp.xn[1], a.ga.H), unnormalise(sp.xn[2], a.ga.D), vm, a.C, N, nq);
-    publish_and_issue([&] {
-      for (int l = 0; l < 5; ++l) mma(32u * l, O_WC + (uint32_t)l * 2u * bbytes(CD), CD, 0, 0u);
-    });
-    if (CD == 64) {
-      gather16(a.gb, unnormalise(sp.xn[0], a.gb.W), unnormalise(sp.xn[1], a.gb.H), unnormalise(sp.xn[2], a.gb.D), vm,
-               a.C ? a.C + (int64_t)32 * N : nullptr, N, nq);
-      publish_and_issue([&] {
-        for (int l = 0; l < 5; ++l) mma(32u * l, O_WC + (uint32_t)l * 2u * bbytes(CD), CD, 1, 1u);
-      });
+    {
+      float4 f[4];
+      gather16(a.ga, unnormalise(sp.xn[0], a.ga.W), unnormalise(sp.xn[1], a.ga.H), unnormalise(sp.xn[2], a.ga.D), vm, a.C, N, nq, f);
+      put_rows(f);
+      publish_issue([&] { mma(0u, O_WC, 5u * bbytes(CD), CD, 0, idesc160, 0u); });
+      if (CD == 64) {   // second grid: gathered while the first product runs
+        gather16(a.gb, unnormalise(sp.xn[0], a.gb.W), unnormalise(sp.xn[1], a.gb.H), unnormalise(sp.xn[2], a.gb.D), vm,
+                 a.C ? a.C + (int64_t)32 * N : nullptr, N, nq, f);
+        wait_mma();
+        put_rows(f);
+        publish_issue([&] { mma(0u, O_WC, 5u * bbytes(CD), CD, 1, idesc160, 1u); });
+      }
     }
-    // ---- Fourier embedding, three K-chunks of 32 (16 columns per thread)
+    // ---- Fourier embedding, three K-chunks of 32 (16 columns per thread); chunk c+1 is computed
+    //      while the product of chunk c (or of the features) is in flight
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       float e[16];
@@ -865,23 +838,37 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
         for (int q = 0; q < 4; ++q)
           o[(int64_t)(8 * c + 4 * half + q) * N + n] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
       }
+      wait_mma();
       store_half_row(e);
-      publish_and_issue([&] { mma(160u, O_W0, 96, c, c > 0 ? 1u : 0u); mma(192u, O_W3E, 96, c, c > 0 ? 1u : 0u); });
+      publish_issue([&] { mma(160u, O_WE, 2u * bbytes(96), 96, c, idesc64, c > 0 ? 1u : 0u); });   // D1_0 and D1_3
     }
-    // ---- blocks 0..3: each thread finishes its 16 columns
+    // ---- blocks 0..3: each thread finishes its 16 columns; s2 = D2_l + bc_l is read ahead of the wait
+    float s2[16];
+    {
+      float d2[16];
+      tmem_ld16(tm_lane + col0, d2);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s2[j] = d2[j] + sm[S_BC + col0 + j];
+    }
+    wait_mma();
 #pragma unroll 1
     for (int l = 0; l < 4; ++l) {
-      float d1[16], d2[16], h[16];
+      float d1[16], h[16];
       const uint32_t c1 = (l == 0) ? 160u : (l == 3 ? 192u : 224u);
       tmem_ld16(tm_lane + c1 + col0, d1);
-      tmem_ld16(tm_lane + 32u * l + col0, d2);
       uint32_t bits = 0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float pre = d1[j] + sm[S_BIAS + l * 32 + col0 + j];
         bits |= (pre > 0.f) ? (1u << j) : 0u;
-        h[j] = fmaxf(pre, 0.f) + (d2[j] + sm[S_BC + l * 32 + col0 + j]);
+        h[j] = fmaxf(pre, 0.f) + s2[j];
       }
+      store_half_row(h);
+      publish_issue([&] {
+        if (l == 2) mma(192u, O_WH + 4 * bbytes(32), bbytes(32), 32, 0, idesc32, 1u);          // D1_3 += W3[:, 93:] . h2
+        else mma(224u, O_WH + (uint32_t)(l == 3 ? 6 : 2 * l) * bbytes(32), bbytes(32), 32, 0, idesc32, 0u);  // W1, W2, W4
+      });
+      // stash + the next block's feature term, under the product
       if (valid) {
         if (a.relu_bits) reinterpret_cast<uint16_t*>(a.relu_bits)[((int64_t)l * N + n) * 2 + half] = (uint16_t)bits;
         if (a.H) {
@@ -890,11 +877,13 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
           for (int q = 0; q < 4; ++q) o[(int64_t)(4 * half + q) * N + n] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
         }
       }
-      store_half_row(h);
-      publish_and_issue([&] {
-        if (l == 2) mma(192u, O_WH + 4 * bbytes(32), 32, 0, 1u);          // D1_3 += W3[:, 93:] . h2
-        else mma(224u, O_WH + (uint32_t)(l == 3 ? 6 : 2 * l) * bbytes(32), 32, 0, 0u);  // W1, W2, W4
-      });
+      if (l < 3) {
+        float d2[16];
+        tmem_ld16(tm_lane + 32u * (l + 1) + col0, d2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s2[j] = d2[j] + sm[S_BC + (l + 1) * 32 + col0 + j];
+      }
+      wait_mma();
     }
     // ---- block 4 + output layer: half 0 finishes the whole row (32 columns)
     if (half == 0) {
@@ -990,7 +979,7 @@ constexpr uint32_t O_A = O_W3ET + 2 * kBE;     // 2 groups x (hi, lo)
 constexpr uint32_t O_SMALL = O_A + kGroups * 2 * kABytes;
 constexpr int S_B = 0, S_WO = 288, S_TOTAL = 416;  // floats
 constexpr uint32_t kSmem = O_SMALL + S_TOTAL * 4u + 40u;
-constexpr int kTileLd = 33;                    // padded row of the feature-gradient tile (reuses the A buffer)
+constexpr int kTileLd = 36;                    // padded row of the feature-gradient tile (reuses the A buffer; 16-byte aligned rows)
 
 // B operand = transpose of a row-major [32 x ld] weight block: element (n, j) = src[j*ld + col0 + n], n < nrows
 __device__ __forceinline__ void stage_bt(unsigned char* hi, uint32_t copy_bytes, const float* __restrict__ src, int ld, int col0,
@@ -1021,7 +1010,7 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 8);
   unsigned char* a_hi = smraw + O_A + (uint32_t)grp * 2u * kABytes;
   unsigned char* a_lo = a_hi + kABytes;
-  float* gtile = reinterpret_cast<float*>(a_hi);   // [128][33] floats, valid between the last MMA and the next tile
+  float* gtile = reinterpret_cast<float*>(a_hi);   // [128][36] floats, valid between the last MMA and the next tile
   if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) { for (int i = 0; i < kGroups; ++i) umma::mbar_init(&bars[i], 1); umma::fence_mbar_init(); }
   stage_bt(smraw + O_WT, kBB, a.w.W[1], 32, 0, 32, 32);
@@ -1163,63 +1152,64 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
       float gc[16];
       tmem_ld16(tm_lane + col0, gc);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) gtile[row * kTileLd + col0 + j] = gc[j];
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(gtile + row * kTileLd + col0 + 4 * q) = make_float4(gc[4 * q], gc[4 * q + 1], gc[4 * q + 2], gc[4 * q + 3]);
       umma::tc_fence_before();
       group_bar();
-      // warp (quarter, half) scatters rows 32*quarter + 16*half + [0,16); lane = channel
+      // warp (quarter, half) scatters rows 32*quarter + 16*half + [0,16): 8 lanes per sample (lane&7 = channel
+      // quad, 128-bit vector reductions), 4 samples per iteration
       const GridDev& g = a.ga;
       const float ux = unnormalise(sp.xn[0], g.W), uy = unnormalise(sp.xn[1], g.H), uz = unnormalise(sp.xn[2], g.D);
-      const float* gd = g.data + lane;
-      int64_t run_base = -1;
-      unsigned run_ok = 0;
-      float run[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) run[k] = 0.f;
+      const int q = lane & 7, sub = lane >> 3;
       float dux = 0.f, duy = 0.f, duz = 0.f;
-      for (int i = 0; i < 16; ++i) {
-        const int src = 16 * half + i;
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it) {
+        const int src = 16 * half + 4 * it + sub;
         const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
-        if (!((vm >> src) & 1u)) continue;
-        const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
-        const float gcv = gtile[(quarter * 32 + src) * kTileLd + lane];
-        if (GRID_GRAD) {
-          if (c.base != run_base) {
-            if (run_base >= 0) {
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if ((vm >> src) & 1u) {
+          const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
+          const float4 gv = *reinterpret_cast<const float4*>(gtile + (quarter * 32 + src) * kTileLd + 4 * q);
+          if (GRID_GRAD) {
+            float* gg = a.g_grid + c.base + 4 * q;
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if ((run_ok >> k) & 1u) atomicAdd(a.g_grid + run_base + corner_offset(k, g.W, g.H) + lane, run[k]);
+            for (int k = 0; k < 8; ++k) {
+              if ((c.ok >> k) & 1u) {
+                const float w = corner_weight(c, k);
+                red_add_v4(gg + corner_offset(k, g.W, g.H), w * gv.x, w * gv.y, w * gv.z, w * gv.w);
+              }
             }
-            run_base = c.base; run_ok = c.ok;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) run[k] = 0.f;
           }
+          if (NEED_DP) {
+            const float4* gd = reinterpret_cast<const float4*>(g.data + c.base) + q;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) run[k] = fmaf(corner_weight(c, k), gcv, run[k]);
+            for (int k = 0; k < 8; ++k) {
+              if ((c.ok >> k) & 1u) {
+                const float4 f = __ldg(gd + corner_offset(k, g.W, g.H) / 4);
+                const float v = fmaf(f.w, gv.w, fmaf(f.z, gv.z, fmaf(f.y, gv.y, f.x * gv.x)));
+                const float wx = c.wx[k & 1], wy = c.wy[(k >> 1) & 1], wz = c.wz[k >> 2];
+                gx += ((k & 1) ? v : -v) * wy * wz;
+                gy += (((k >> 1) & 1) ? v : -v) * wx * wz;
+                gz += ((k >> 2) ? v : -v) * wx * wy;
+              }
+            }
+            gx *= c.gm[0]; gy *= c.gm[1]; gz *= c.gm[2];
+          }
         }
         if (NEED_DP) {
-          float gx = 0.f, gy = 0.f, gz = 0.f;
+          // sum over the sample's 8 lanes, then hand the result to the lane that owns the row
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if ((c.ok >> k) & 1u) {
-              const float v = __ldg(gd + c.base + corner_offset(k, g.W, g.H));
-              const float wx = c.wx[k & 1], wy = c.wy[(k >> 1) & 1], wz = c.wz[k >> 2];
-              gx += ((k & 1) ? v : -v) * wy * wz;
-              gy += (((k >> 1) & 1) ? v : -v) * wx * wz;
-              gz += ((k >> 2) ? v : -v) * wx * wy;
-            }
+          for (int o = 4; o > 0; o >>= 1) {
+            gx += __shfl_xor_sync(kFull, gx, o); gy += __shfl_xor_sync(kFull, gy, o); gz += __shfl_xor_sync(kFull, gz, o);
           }
-          gx = warp_sum(gx * gcv); gy = warp_sum(gy * gcv); gz = warp_sum(gz * gcv);
-          if (lane == src) { dux = gx * c.gm[0]; duy = gy * c.gm[1]; duz = gz * c.gm[2]; }
+          const int from = 8 * (lane & 3);
+          const float rx = __shfl_sync(kFull, gx, from), ry = __shfl_sync(kFull, gy, from), rz = __shfl_sync(kFull, gz, from);
+          if (lane == 16 * half + 4 * it + (lane & 3)) { dux = rx; duy = ry; duz = rz; }
         }
-      }
-      if (GRID_GRAD && run_base >= 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if ((run_ok >> k) & 1u) atomicAdd(a.g_grid + run_base + corner_offset(k, g.W, g.H) + lane, run[k]);
       }
       if (NEED_DP) {
         // rows 16*half..16*half+15 of this quarter got their grid-path gradient in lanes 16*half + i of THIS warp;
-        // combine with the embedding path: half 0 holds gp of its own columns, half 1 left its share in the tile
+        // combine with the embedding path: each (row, half) thread holds gp of its own 16 embedding columns
         const bool mine = (lane >> 4) == half;   // this lane's row was scattered by this warp
         if (mine && valid) {
           gp[0] += norm_grad(a.pts, a.nb, 0, dux); gp[1] += norm_grad(a.pts, a.nb, 1, duy); gp[2] += norm_grad(a.pts, a.nb, 2, duz);
