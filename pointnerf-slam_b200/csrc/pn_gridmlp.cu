@@ -959,25 +959,29 @@ int launch_fwd(const FwdArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // backward (input gradients) on the tensor cores
 // ---------------------------------------------------------------------------
-// Same tiling as the forward: CTA = 2 groups x 256 threads, two threads per sample row.
+// Same tiling as the forward: CTA = 3 groups x 256 threads, two threads per sample row.
 // Every transposed mat-vec of the FFMA kernel becomes D[128 x N] (+)= G[128 x 32] . (W^T)[N x 32]^T
 // with the gradient operand G (hi/lo) in the group's shared buffer and the transposed weights
 // pre-split in shared memory.  Tensor-memory columns per group:
-//     0..31   D_gc = sum_l gh_l . Wc_l[:, :32]      (feature gradient, accumulated over blocks)
-//    32..63   D_x  = ga_l . W_l                     (gradient at the previous block's output)
+//     0..31   D_gc = feature gradient, accumulated over blocks
+//    32..63   D_x  = ga_l . W_l                     (gradient gh_{l-1} at the previous block's output)
 //    64..159  D_ge = ga_3 . W3[:, :93] + ga_0 . W0  (gradient at the Fourier embedding)
+// One tensor-core round trip per block: the feature gradient sum_l gh_l . Wc_l is rewritten with
+// gh_{l-1} = ga_l . W_l as  go . (Wo Wc_4) + sum_{l>=1} ga_l . (W_l Wc_{l-1}),  so the SAME operand ga_l
+// feeds both products of a block (the weight products M_{l-1} = W_l Wc_{l-1} are formed once per
+// CTA while staging; the go term is four FMAs per column in registers).
 namespace tcb {
 using tc::kLbo; using tc::kASbo; using tc::kABytes;
 constexpr int kGroups = 3;                     // independent 128-sample tiles in flight per CTA (160 TMEM columns each)
 constexpr uint32_t kBB = 4096;                 // one [32 x 32] operand copy
 constexpr uint32_t kBE = 12288;                // one [96 x 32] operand copy
 constexpr uint32_t O_WT = 0;                   // W1^T, W2^T, W3h^T, W4^T (hi, lo each)
-constexpr uint32_t O_WCT = O_WT + 8 * kBB;     // Wc_l[:, :32]^T, l = 0..4
-constexpr uint32_t O_W0T = O_WCT + 10 * kBB;   // W0^T  [96 x 32]
+constexpr uint32_t O_WCT = O_WT + 8 * kBB;     // M_m^T = (W_{m+1} Wc_m[:, :32])^T, m = 0..3
+constexpr uint32_t O_W0T = O_WCT + 8 * kBB;    // W0^T  [96 x 32]
 constexpr uint32_t O_W3ET = O_W0T + 2 * kBE;   // W3[:, :93]^T
 constexpr uint32_t O_A = O_W3ET + 2 * kBE;     // 2 groups x (hi, lo)
 constexpr uint32_t O_SMALL = O_A + kGroups * 2 * kABytes;
-constexpr int S_B = 0, S_WO = 288, S_TOTAL = 416;  // floats
+constexpr int S_B = 0, S_WO = 288, S_WOC = 416, S_TOTAL = 544;  // floats
 constexpr uint32_t kSmem = O_SMALL + S_TOTAL * 4u + 40u;
 constexpr int kTileLd = 36;                    // padded row of the feature-gradient tile (reuses the A buffer; 16-byte aligned rows)
 
@@ -991,6 +995,22 @@ __device__ __forceinline__ void stage_bt(unsigned char* hi, uint32_t copy_bytes,
     float h, l;
     umma::split_tf32(w, h, l);
     const uint32_t off = umma::kmajor_off(n, j, kLbo, 1024u);
+    *reinterpret_cast<float*>(hi + off) = h;
+    *reinterpret_cast<float*>(lo + off) = l;
+  }
+}
+
+// B operand = transpose of the weight product M = Wl[:, colw .. colw+31] . Wc[:, :32]   ([32 x 32], FP32 sums)
+__device__ __forceinline__ void stage_prod_t(unsigned char* hi, uint32_t copy_bytes, const float* __restrict__ Wl, int ldw, int colw,
+                                             const float* __restrict__ Wc, int cd) {
+  unsigned char* lo = hi + copy_bytes;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const int k = i >> 5, n = i & 31;
+    float m = 0.f;
+    for (int t = 0; t < 32; ++t) m = fmaf(Wl[k * ldw + colw + t], Wc[t * cd + n], m);
+    float h, l;
+    umma::split_tf32(m, h, l);
+    const uint32_t off = umma::kmajor_off(n, k, kLbo, 1024u);
     *reinterpret_cast<float*>(hi + off) = h;
     *reinterpret_cast<float*>(lo + off) = l;
   }
@@ -1017,7 +1037,20 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
   stage_bt(smraw + O_WT + 2 * kBB, kBB, a.w.W[2], 32, 0, 32, 32);
   stage_bt(smraw + O_WT + 4 * kBB, kBB, a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
   stage_bt(smraw + O_WT + 6 * kBB, kBB, a.w.W[4], 32, 0, 32, 32);
-  for (int l = 0; l < 5; ++l) stage_bt(smraw + O_WCT + (uint32_t)l * 2u * kBB, kBB, a.w.Wc[l], CD, 0, 32, 32);
+  constexpr bool GC = GRID_GRAD || NEED_DP;
+  if (GC) {
+    stage_prod_t(smraw + O_WCT, kBB, a.w.W[1], 32, 0, a.w.Wc[0], CD);
+    stage_prod_t(smraw + O_WCT + 2 * kBB, kBB, a.w.W[2], 32, 0, a.w.Wc[1], CD);
+    stage_prod_t(smraw + O_WCT + 4 * kBB, kBB, a.w.W[3], PN_EMBED + 32, PN_EMBED, a.w.Wc[2], CD);
+    stage_prod_t(smraw + O_WCT + 6 * kBB, kBB, a.w.W[4], 32, 0, a.w.Wc[3], CD);
+    for (int i = tid; i < 128; i += blockDim.x) {   // (Wo Wc_4)[o][j]
+      const int o = i >> 5, j = i & 31;
+      float m = 0.f;
+      if (o < NOUT)
+        for (int t = 0; t < 32; ++t) m = fmaf(a.w.Wo[o * 32 + t], a.w.Wc[4][t * CD + j], m);
+      sm[S_WOC + i] = m;
+    }
+  }
   if (EMB) {
     stage_bt(smraw + O_W0T, kBE, a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
     stage_bt(smraw + O_W3ET, kBE, a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
@@ -1099,18 +1132,12 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
     }
     // the previous tile's scatter phase used the A buffer as a scratch tile: all of the group must be done with it
     group_bar();
+    uint32_t bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)4 * N + n) * 2 + half] : 0u;
 #pragma unroll 1
     for (int l = 4; l >= 0; --l) {
       if (WS && valid) stash_half(a.GH + (int64_t)l * 32 * N, N, n, gh);
-      if (GRID_GRAD || NEED_DP) {
-        store_half_row(gh);
-        publish_issue([&] { mma(0u, O_WCT + (uint32_t)l * 2u * kBB, kBB, idesc32, l < 4 ? 1u : 0u); });
-      }
-      const uint32_t bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)l * N + n) * 2 + half] : 0u;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) gh[j] = ((bits >> j) & 1u) ? gh[j] : 0.f;
-      if (WS && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);
-      if (GRID_GRAD || NEED_DP) wait_mma();
+      for (int j = 0; j < 16; ++j) gh[j] = ((bits >> j) & 1u) ? gh[j] : 0.f;    // ga_l
       if (l > 0 || EMB) {
         store_half_row(gh);
         publish_issue([&] {
@@ -1119,7 +1146,13 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
           else if (l == 2) mma(32u, O_WT + 2 * kBB, kBB, idesc32, 0u);
           else if (l == 1) mma(32u, O_WT, kBB, idesc32, 0u);
           else mma(64u, O_W0T, kBE, idesc96, 1u);
+          if (GC && l > 0) mma(0u, O_WCT + (uint32_t)(l - 1) * 2u * kBB, kBB, idesc32, l < 4 ? 1u : 0u);   // D_gc (+)= ga_l . M_{l-1}
         });
+      }
+      // under the products: stash, next block's ReLU bits
+      if (WS && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);
+      if (l > 0) bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)(l - 1) * N + n) * 2 + half] : 0u;
+      if (l > 0 || EMB) {
         wait_mma();
         if (l > 0) tmem_ld16(tm_lane + 32u + col0, gh);
       }
@@ -1151,6 +1184,11 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
     if (GRID_GRAD || NEED_DP) {
       float gc[16];
       tmem_ld16(tm_lane + col0, gc);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) gc[j] = fmaf(sm[S_WOC + o * 32 + col0 + j], go[o], gc[j]);   // gh_4 . Wc_4
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         *reinterpret_cast<float4*>(gtile + row * kTileLd + col0 + 4 * q) = make_float4(gc[4 * q], gc[4 * q + 1], gc[4 * q + 2], gc[4 * q + 3]);

@@ -1,7 +1,7 @@
 // Weight gradients of a grid decoder on the tensor cores.
 //
 // dW[j][f] = sum_n G[n][j] * X[n][f] is a GEMM whose reduction runs over SAMPLES: the sample
-// axis is the MMA K dimension, features (M = 128) and outputs (N = 32) are the rows of the two
+// axis is the MMA K dimension, features (M = 128) and outputs (N = 32 per block) are the rows of the two
 // operands.  The operands are read from the planar-4 stash ([feature/4][sample] float4, coalesced
 // 256-byte rows per 16-sample chunk), split into TF32 hi/lo in registers and stored TRANSPOSED
 // into the canonical K-major no-swizzle layout
@@ -11,14 +11,15 @@
 // (The MN-major operand mode, which would take the stash rows unchanged, returns zeros for
 // kind::tf32 on sm_100a -- measured with pn_tc_selftest_mn -- so it is not used.)
 //
-// Per 16-sample chunk (K = 16 = 2 MMA k-steps), M = 128 features, N = 32 outputs, 3xTF32:
-//     A_H = [h0|h1|h2|h3]   x GA_1..GA_4  -> dW1, dW2, dW3[:, 93:], dW4 (diagonal 32-row blocks)
-//     A_E = [emb(96)|0(32)] x GA_0, GA_3  -> dW0, dW3[:, :93]
-//     A_C = [c(CD)|0]       x GH_0..GH_4  -> dWc_0..4
+// Per 16-sample chunk (K = 16 = 2 MMA k-steps), M = 128 features, 3xTF32, one wide-N product per A operand:
+//     A_H = [h0|h1|h2|h3]   x [GA_3|GA_1|GA_2|GA_4] (N = 128) -> dW3[:, 93:], dW1, dW2, dW4 (diagonal 32-row blocks)
+//     A_E = [emb(96)|0(32)] x [GA_0|GA_3]           (N = 64)  -> dW0, dW3[:, :93]
+//     A_C = [c(CD)|0]       x [GH_0..GH_4]          (N = 160) -> dWc_0..4
 // 11 FP32 accumulators (352 tensor-memory columns) stay resident for the whole kernel; each CTA
 // flushes them once with atomics.  Two operand stages alternate: while the tensor core works on
-// chunk i, the 512 threads load / split / transpose chunk i+1 (an mbarrier per stage, armed by
-// tcgen05.commit, says when a stage may be overwritten).  Bias gradients (column sums of GA_l /
+// chunk i, the 512 threads split / transpose chunk i+1 (an mbarrier per stage, armed by
+// tcgen05.commit, says when a stage may be overwritten), and the global loads of chunk i+2 are
+// already in flight in registers.  Bias gradients (column sums of GA_l /
 // GH_l) are accumulated by the loading threads on the side.
 #include "pn_common.cuh"
 #include "pn_umma.cuh"
@@ -110,37 +111,44 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgTcArgs a) {
   const float4* GA4 = reinterpret_cast<const float4*>(a.GA);
   const float4* GH4 = reinterpret_cast<const float4*>(a.GH);
   const int64_t nchunks = (N + kChunk - 1) / kChunk;
+  // this thread's share of one chunk: up to six 16-byte loads (coalesced 256-byte rows per half-warp)
+  struct Regs { float4 vh, ve, vc, vg[3]; };
+  auto load_chunk = [&](int64_t c, Regs& r) {
+    const int64_t n = c * kChunk + s;
+    const bool ok = c < nchunks && n < N;
+    r.vh = ok ? H4[(int64_t)slot * N + n] : z4;                       // [h0|h1|h2|h3]: quad = slot
+    r.ve = (ok && slot < 24) ? E4[(int64_t)slot * N + n] : z4;
+    r.vc = (ok && slot < cq) ? C4[(int64_t)slot * N + n] : z4;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int row = i * 32 + slot;             // 0..79: GA_0..4 (rows 0..39), GH_0..4 (40..79)
+      r.vg[i] = z4;
+      if (ok && row < 80) r.vg[i] = row < 40 ? GA4[(int64_t)row * N + n] : GH4[(int64_t)(row - 40) * N + n];
+    }
+  };
   int it = 0;
+  Regs cur, nxt;
+  load_chunk(blockIdx.x, cur);
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
     const int st = it & 1;
     unsigned char* base = smraw + st * kStage;
-    const int64_t n = c * kChunk + s;
-    const bool ok = n < N;
-    // global loads first (they do not touch shared memory), then wait for the stage to be free
-    const float4 vh = ok ? H4[(int64_t)slot * N + n] : z4;                       // [h0|h1|h2|h3]: quad = slot
-    const float4 ve = (ok && slot < 24) ? E4[(int64_t)slot * N + n] : z4;
-    const float4 vc = (ok && slot < cq) ? C4[(int64_t)slot * N + n] : z4;
-    float4 vg[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int row = r * 32 + slot;             // 0..79: GA_0..4 (rows 0..39), GH_0..4 (40..79)
-      vg[r] = z4;
-      if (ok && row < 80) vg[r] = row < 40 ? GA4[(int64_t)row * N + n] : GH4[(int64_t)(row - 40) * N + n];
-    }
+    // the next chunk's global loads are in flight while this chunk is split, transposed and multiplied
+    load_chunk(c + gridDim.x, nxt);
     if (it >= 2) { umma::mbar_wait(&bars[st], phase[st]); phase[st] ^= 1u; umma::tc_fence_after(); }
-    put_split(base + O_AH, kACopy, slot, s, vh);
-    if (slot < 24) put_split(base + O_AE, kACopy, slot, s, ve);
-    if (slot < cq) put_split(base + O_AC, kACopy, slot, s, vc);
+    put_split(base + O_AH, kACopy, slot, s, cur.vh);
+    if (slot < 24) put_split(base + O_AE, kACopy, slot, s, cur.ve);
+    if (slot < cq) put_split(base + O_AC, kACopy, slot, s, cur.vc);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int row = r * 32 + slot;
       if (row < 80) {
         const int arr = row >> 3;                                        // GA_l = l, GH_l = 5 + l
         const int pos = arr == 1 ? 2 : arr == 2 ? 3 : arr == 3 ? 1 : arr;  // position in shared memory
-        put_split(base + O_B + (uint32_t)pos * kBCopy, kBLo, row & 7, s, vg[r]);
-        bsum[r].x += vg[r].x; bsum[r].y += vg[r].y; bsum[r].z += vg[r].z; bsum[r].w += vg[r].w;
+        put_split(base + O_B + (uint32_t)pos * kBCopy, kBLo, row & 7, s, cur.vg[r]);
+        bsum[r].x += cur.vg[r].x; bsum[r].y += cur.vg[r].y; bsum[r].z += cur.vg[r].z; bsum[r].w += cur.vg[r].w;
       }
     }
+    cur = nxt;
     umma::fence_proxy_async();
     umma::tc_fence_before();
     __syncthreads();
