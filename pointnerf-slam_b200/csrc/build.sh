@@ -9,7 +9,11 @@ mkdir -p "$HERE/obj"
 pids=()
 for f in "$HERE"/*.cu; do
   o="$HERE/obj/$(basename "${f%.cu}").o"
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/pn_common.cuh" -nt "$o" || "$ROOT/include/pnslam.h" -nt "$o" ]]; then
+  stale=0
+  for dep in "$f" "$HERE"/*.cuh "$ROOT/include/pnslam.h"; do
+    if [[ ! -f "$o" || "$dep" -nt "$o" ]]; then stale=1; fi
+  done
+  if [[ $stale == 1 ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" &
     pids+=($!)
   fi

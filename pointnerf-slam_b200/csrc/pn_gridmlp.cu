@@ -18,10 +18,7 @@
 //   * MLP phase, thread = sample: activations live in registers, weights are
 //     staged once per CTA in shared memory ([out][in] rows, 16-byte aligned)
 //     and read as warp-uniform LDS.128 broadcasts.
-#include <stdlib.h>
-
-#include "pn_common.cuh"
-#include "pn_umma.cuh"
+#include "pn_gridmlp.cuh"
 
 namespace pn {
 namespace {
@@ -40,17 +37,6 @@ constexpr int OFF_WC = OFF_BO + 4;         // [5][32][CD]
 static_assert(OFF_WC % 4 == 0, "alignment");
 template <int CD> __host__ __device__ constexpr int wfloats() { return OFF_WC + 5 * 32 * CD; }
 template <int CD> __host__ __device__ constexpr size_t smem_bytes() { return (size_t)(wfloats<CD>() + CD * kLdc) * sizeof(float); }
-
-struct MlpDev {  // device copy of pn_grid_mlp pointers
-  const float* B; const float* W[5]; const float* b[5]; const float* Wc[5]; const float* bc[5];
-  const float* Wo; const float* bo;
-};
-inline MlpDev make_mlp(const pn_grid_mlp* w) {
-  MlpDev m;
-  m.B = w->B; m.Wo = w->Wo; m.bo = w->bo;
-  for (int i = 0; i < 5; ++i) { m.W[i] = w->W[i]; m.b[i] = w->b[i]; m.Wc[i] = w->Wc[i]; m.bc[i] = w->bc[i]; }
-  return m;
-}
 
 template <int CD, int NOUT>
 __device__ void stage_weights(const MlpDev& m, float* wsm) {
@@ -123,12 +109,6 @@ __device__ __forceinline__ void feature_term(const float* __restrict__ Wc, const
       acc[j] = fmaf(w.w, c3, acc[j]);
     }
   }
-}
-
-__device__ __forceinline__ void store_planar32(float* base, int64_t N, int64_t n, const float (&v)[32]) {
-  float4* o = reinterpret_cast<float4*>(base);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) o[(int64_t)q * N + n] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // ---------------------------------------------------------------------------
@@ -216,16 +196,6 @@ __device__ __forceinline__ void warp_scatter(const GridDev& g, float* __restrict
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-struct FwdArgs {
-  pn_points pts;
-  MlpDev w;
-  GridDev ga, gb;
-  Bound6 nb, mb;
-  int apply_mask, out_mode;
-  float* raw;
-  uint32_t* relu_bits; float* H; float* C; float* E;
-};
-
 template <int CD, int NOUT>
 __global__ void __launch_bounds__(kThreads, CD == 32 ? 2 : 1) k_grid_mlp_fwd(const FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -329,18 +299,6 @@ __global__ void __launch_bounds__(kThreads, CD == 32 ? 2 : 1) k_grid_mlp_fwd(con
 // ---------------------------------------------------------------------------
 // backward w.r.t. activations / features / points
 // ---------------------------------------------------------------------------
-struct BwdArgs {
-  pn_points pts;
-  MlpDev w;
-  GridDev ga, gb;
-  Bound6 nb, mb;
-  int apply_mask, accumulate_pts;
-  const float* g_raw;
-  const uint32_t* relu_bits;
-  float* g_grid; float* g_pts;
-  float* GA; float* GH; float* GARG; float* P32; float* GO;
-};
-
 template <int CD, int NOUT, bool GRID_GRAD, bool NEED_DP, bool WS>
 __global__ void __launch_bounds__(kThreads, 1) k_grid_mlp_bwd(const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -605,347 +563,9 @@ __global__ void __launch_bounds__(768) k_wgrad_B(const float* __restrict__ P32, 
     }
 }
 
-// ---------------------------------------------------------------------------
-// forward on the 5th-gen tensor cores (tcgen05, kind::tf32, 3xTF32 split)
-// ---------------------------------------------------------------------------
-// CTA = 512 threads = two independent groups of 256; a group owns one tile of 128 consecutive
-// samples at a time (two threads per sample row = TMEM lane, 16 columns each).  Per tile every
-// decoder layer is a D[128 x N] (+)= A[128 x 32] . W[N x 32]^T tensor-core product: the activation
-// operand A is written by the group (hi and lo copies, canonical K-major layout) into its 32 KB
-// shared buffer, the weights sit pre-split in shared memory for the whole kernel, the accumulators
-// live in the group's 256 tensor-memory columns:
-//     cols   0..159  D2_l = Wc_l . c           (feature terms of all five blocks: ONE N=160 product)
-//     cols 160..191  D1_0 = W0 . emb           (3 K-chunks of 32; D1_0 and D1_3 are ONE N=64 product)
-//     cols 192..223  D1_3 = W3[:, :93] . emb + W3[:, 93:] . h2
-//     cols 224..255  D1_x = W_l . h_{l-1}      (blocks 1, 2, 4)
-// The epilogue of a block reads its accumulators back (tcgen05.ld), applies
-// relu(D1 + b) + D2 + bc in registers, re-splits into hi/lo and stores the next A operand.
-// Everything that does not depend on the product in flight -- the next chunk's sines, the second
-// grid's gather, the stash stores, the next block's D2 + bc -- is done between issuing the MMAs
-// and waiting for them; while one group waits the other group runs.
-namespace tc {
-constexpr uint32_t kLbo = 128;                       // core matrices adjacent in K
-constexpr uint32_t kASbo = 8 * 128;                  // A buffer: K = 32 per 8-row group
-constexpr uint32_t kABytes = 16 * kASbo;             // one 128 x 32 operand copy (16 KB)
-__host__ __device__ constexpr uint32_t bsbo(int K) { return (uint32_t)(K / 4) * 128u; }
-__host__ __device__ constexpr uint32_t bbytes(int K) { return 4u * bsbo(K); }  // 32 rows
-// byte offsets of the pre-split weight operands
-constexpr uint32_t O_WE = 0;                         // [W0; W3[:, :93]] as one [64 x 96] operand: hi, then lo
-constexpr uint32_t O_WH = O_WE + 4 * bbytes(96);     // 4 x [32 x 32]: hi, lo per block
-template <int CD> __host__ __device__ constexpr uint32_t o_wc() { return O_WH + 4 * 2 * bbytes(32); }   // [160 x CD]: hi, then lo
-template <int CD> __host__ __device__ constexpr uint32_t o_a() { return o_wc<CD>() + 5u * 2u * bbytes(CD); }   // A buffers
-template <int CD> __host__ __device__ constexpr uint32_t o_small() { return o_a<CD>() + 2u * 2u * kABytes; }
-constexpr int S_B = 0, S_BIAS = 288, S_BC = 448, S_WO = 608, S_BO = 736, S_TOTAL = 740;  // floats
-// the two mbarriers and the TMEM base address follow the float area (kept in dynamic shared
-// memory: with c_dim 64 the kernel uses all but ~100 bytes of the 227 KB an SM offers)
-template <int CD> __host__ __device__ constexpr uint32_t smem_total() { return o_small<CD>() + S_TOTAL * 4u + 24u; }
-
-// split a [32 x K] row-major weight block (row stride ld, starting column col0, `kvalid` real
-// columns, zero beyond) into canonical hi / lo operands
-__device__ __forceinline__ void stage_b(unsigned char* hi, unsigned char* lo, const float* __restrict__ src, int ld, int col0, int K,
-                                        int kvalid) {
-  for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
-    const int n = i / K, k = i - n * K;
-    const float w = k < kvalid ? src[n * ld + col0 + k] : 0.f;
-    float h, l;
-    umma::split_tf32(w, h, l);
-    const uint32_t off = umma::kmajor_off(n, k, kLbo, bsbo(K));
-    *reinterpret_cast<float*>(hi + off) = h;
-    *reinterpret_cast<float*>(lo + off) = l;
-  }
-}
-}  // namespace tc
-
-// 128-bit vector reduction into global memory (sm_90+): four float atomics in one instruction
-__device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-
-// TMEM -> registers, 16 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// CTA = 512 threads = two groups of 256.  Inside a group TWO threads serve each of the 128
-// sample rows: warp (quarter q = warp&3, half = warp>>2) owns rows 32q..32q+31 (the TMEM lanes
-// a warp with that id may address) and columns [16*half, 16*half+16) of every 32-wide operand.
-template <int CD, int NOUT>
-__global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
-  extern __shared__ __align__(128) unsigned char smraw[];
-  using namespace tc;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int grp = tid >> 8, gw = (tid >> 5) & 7, quarter = gw & 3, half = gw >> 2;
-  const int row = quarter * 32 + lane, col0 = 16 * half;
-  float* sm = reinterpret_cast<float*>(smraw + o_small<CD>());
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S_TOTAL);
-  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 4);
-  unsigned char* a_hi = smraw + o_a<CD>() + (uint32_t)grp * 2u * kABytes;
-  unsigned char* a_lo = a_hi + kABytes;
-  // ---- one-time set-up: TMEM, barriers, weights
-  if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
-  if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
-  constexpr uint32_t O_WC = o_wc<CD>();
-  stage_b(smraw + O_WE, smraw + O_WE + 2 * bbytes(96), a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
-  stage_b(smraw + O_WE + bbytes(96), smraw + O_WE + 3 * bbytes(96), a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
-  stage_b(smraw + O_WH, smraw + O_WH + bbytes(32), a.w.W[1], 32, 0, 32, 32);
-  stage_b(smraw + O_WH + 2 * bbytes(32), smraw + O_WH + 3 * bbytes(32), a.w.W[2], 32, 0, 32, 32);
-  stage_b(smraw + O_WH + 4 * bbytes(32), smraw + O_WH + 5 * bbytes(32), a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
-  stage_b(smraw + O_WH + 6 * bbytes(32), smraw + O_WH + 7 * bbytes(32), a.w.W[4], 32, 0, 32, 32);
-  for (int l = 0; l < 5; ++l)
-    stage_b(smraw + O_WC + (uint32_t)l * bbytes(CD), smraw + O_WC + (uint32_t)(5 + l) * bbytes(CD), a.w.Wc[l], CD, 0, CD, CD);
-  for (int i = tid; i < 288; i += 512) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
-  for (int i = tid; i < 160; i += 512) { sm[S_BIAS + i] = a.w.b[i >> 5][i & 31]; sm[S_BC + i] = a.w.bc[i >> 5][i & 31]; }
-  for (int i = tid; i < 128; i += 512) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
-  if (tid < 4) sm[S_BO + tid] = tid < NOUT ? a.w.bo[tid] : 0.f;
-  umma::fence_proxy_async();
-  umma::tc_fence_before();
-  __syncthreads();
-  umma::tc_fence_after();
-  const uint32_t tm = tmem_base_s + (uint32_t)grp * 256u;               // this group's columns
-  const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);        // this warp's lanes
-  const uint32_t sA = umma::smem_u32(a_hi), sAlo = sA + kABytes;
-  const uint32_t sW = umma::smem_u32(smraw);
-  constexpr uint32_t idesc32 = umma::instr_desc_tf32(128, 32), idesc64 = umma::instr_desc_tf32(128, 64),
-                     idesc160 = umma::instr_desc_tf32(128, 160);
-  uint64_t* bar = &bars[grp];
-  uint32_t phase = 0;
-  const bool issuer = (tid & 255) == 0;
-  const uint64_t dA_hi = umma::smem_desc(sA, kLbo, kASbo), dA_lo = umma::smem_desc(sAlo, kLbo, kASbo);
-  constexpr uint32_t kStep = (2u * kLbo) >> 4;   // one K-step of 8 in descriptor address units
-  // D[:, dcol .. dcol+N) (+)= A . B[:, 32*k32 .. 32*k32+31]^T for the [N x Kb] operand whose hi copy
-  // starts at byte offset boff and whose lo copy follows lo_off bytes later
-  auto mma = [&](uint32_t dcol, uint32_t boff, uint32_t lo_off, int Kb, int k32, uint32_t idesc, uint32_t acc) {
-    const uint32_t bh = sW + boff + (uint32_t)k32 * 8u * kLbo;
-    const uint64_t dB_hi = umma::smem_desc(bh, kLbo, bsbo(Kb)), dB_lo = umma::smem_desc(bh + lo_off, kLbo, bsbo(Kb));
-    umma::mma_3xtf32_k32(tm + dcol, dA_hi, dA_lo, dB_hi, dB_lo, kStep, kStep, idesc, acc);
-  };
-  // A written by every thread of the group -> one thread issues the MMAs and commits them to the barrier
-  auto publish_issue = [&](auto&& issue) {
-    umma::fence_proxy_async();
-    umma::tc_fence_before();
-    asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
-    if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
-  };
-  // one lane polls the mbarrier; the other 255 threads of the group sleep on a named barrier
-  auto wait_mma = [&] {
-    if ((tid & 255) < 32) { if (lane == 0) umma::mbar_wait(bar, phase); __syncwarp(); }
-    asm volatile("bar.sync %0, 256;" ::"r"(grp + 4) : "memory");
-    phase ^= 1u;
-    umma::tc_fence_after();
-  };
-  // this thread's 16 columns of its row -> A operand (hi and lo)
-  auto store_half_row = [&](const float (&v)[16]) {
-    const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)(4 * half) * kLbo;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 h, l;
-      umma::split_tf32(v[4 * q], h.x, l.x); umma::split_tf32(v[4 * q + 1], h.y, l.y);
-      umma::split_tf32(v[4 * q + 2], h.z, l.z); umma::split_tf32(v[4 * q + 3], h.w, l.w);
-      *reinterpret_cast<float4*>(a_hi + base + q * kLbo) = h;
-      *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
-    }
-  };
-  // trilinear features of rows 32*quarter + 16*half + [0,16): 8 lanes per sample (lane&7 = channel quad,
-  // 128-bit loads), 4 samples per iteration; the values stay in registers until put_rows
-  auto gather16 = [&](const GridDev& g, float ux, float uy, float uz, unsigned vm, float* __restrict__ Cst, int64_t N, int64_t nq,
-                      float4 (&out)[4]) {
-    const int q = lane & 7, sub = lane >> 3;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int src = 16 * half + 4 * it + sub;   // lane (within this warp) that owns the row
-      const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((vm >> src) & 1u) {
-        const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
-        const float4* gp = reinterpret_cast<const float4*>(g.data + c.base) + q;
-        float4 val[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          val[k] = ((c.ok >> k) & 1u) ? __ldg(gp + corner_offset(k, g.W, g.H) / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if ((c.ok >> k) & 1u) {
-            const float w = corner_weight(c, k);
-            v.x = __fadd_rn(v.x, __fmul_rn(val[k].x, w)); v.y = __fadd_rn(v.y, __fmul_rn(val[k].y, w));
-            v.z = __fadd_rn(v.z, __fmul_rn(val[k].z, w)); v.w = __fadd_rn(v.w, __fmul_rn(val[k].w, w));
-          }
-        }
-        if (Cst) reinterpret_cast<float4*>(Cst)[(int64_t)q * N + nq + src] = v;
-      }
-      out[it] = v;
-    }
-  };
-  auto put_rows = [&](const float4 (&v)[4]) {
-    const int q = lane & 7, sub = lane >> 3;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = quarter * 32 + 16 * half + 4 * it + sub;
-      float4 h, l;
-      umma::split_tf32(v[it].x, h.x, l.x); umma::split_tf32(v[it].y, h.y, l.y);
-      umma::split_tf32(v[it].z, h.z, l.z); umma::split_tf32(v[it].w, h.w, l.w);
-      const uint32_t off = (uint32_t)(r >> 3) * kASbo + (uint32_t)(r & 7) * 16u + (uint32_t)q * kLbo;
-      *reinterpret_cast<float4*>(a_hi + off) = h;
-      *reinterpret_cast<float4*>(a_lo + off) = l;
-    }
-  };
-
-  const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
-  for (int64_t t = (int64_t)blockIdx.x * 2 + grp; t < ntiles; t += (int64_t)gridDim.x * 2) {
-    const int64_t n = t * 128 + row;
-    const bool valid = n < N;
-    Sample sp;
-    sp.pf[0] = sp.pf[1] = sp.pf[2] = 0.f; sp.xn[0] = sp.xn[1] = sp.xn[2] = 0.f; sp.inside = true;
-    if (valid) load_sample(a.pts, n, a.nb, a.mb, sp);
-    const unsigned vm = __ballot_sync(kFull, valid);
-    const int64_t nq = t * 128 + quarter * 32;
-    // ---- feature terms of all five blocks
-    {
-      float4 f[4];
-      gather16(a.ga, unnormalise(sp.xn[0], a.ga.W), unnormalise(sp.xn[1], a.ga.H), unnormalise(sp.xn[2], a.ga.D), vm, a.C, N, nq, f);
-      put_rows(f);
-      publish_issue([&] { mma(0u, O_WC, 5u * bbytes(CD), CD, 0, idesc160, 0u); });
-      if (CD == 64) {   // second grid: gathered while the first product runs
-        gather16(a.gb, unnormalise(sp.xn[0], a.gb.W), unnormalise(sp.xn[1], a.gb.H), unnormalise(sp.xn[2], a.gb.D), vm,
-                 a.C ? a.C + (int64_t)32 * N : nullptr, N, nq, f);
-        wait_mma();
-        put_rows(f);
-        publish_issue([&] { mma(0u, O_WC, 5u * bbytes(CD), CD, 1, idesc160, 1u); });
-      }
-    }
-    // ---- Fourier embedding, three K-chunks of 32 (16 columns per thread); chunk c+1 is computed
-    //      while the product of chunk c (or of the features) is in flight
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-      float e[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int kk = 32 * c + col0 + k;
-        e[k] = fourier_sin(fmaf(sp.pf[2], sm[S_B + 192 + kk], fmaf(sp.pf[1], sm[S_B + 96 + kk], sp.pf[0] * sm[S_B + kk])));
-      }
-      if (a.E && valid) {
-        float4* o = reinterpret_cast<float4*>(a.E);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          o[(int64_t)(8 * c + 4 * half + q) * N + n] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
-      }
-      wait_mma();
-      store_half_row(e);
-      publish_issue([&] { mma(160u, O_WE, 2u * bbytes(96), 96, c, idesc64, c > 0 ? 1u : 0u); });   // D1_0 and D1_3
-    }
-    // ---- blocks 0..3: each thread finishes its 16 columns; s2 = D2_l + bc_l is read ahead of the wait
-    float s2[16];
-    {
-      float d2[16];
-      tmem_ld16(tm_lane + col0, d2);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) s2[j] = d2[j] + sm[S_BC + col0 + j];
-    }
-    wait_mma();
-#pragma unroll 1
-    for (int l = 0; l < 4; ++l) {
-      float d1[16], h[16];
-      const uint32_t c1 = (l == 0) ? 160u : (l == 3 ? 192u : 224u);
-      tmem_ld16(tm_lane + c1 + col0, d1);
-      uint32_t bits = 0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float pre = d1[j] + sm[S_BIAS + l * 32 + col0 + j];
-        bits |= (pre > 0.f) ? (1u << j) : 0u;
-        h[j] = fmaxf(pre, 0.f) + s2[j];
-      }
-      store_half_row(h);
-      publish_issue([&] {
-        if (l == 2) mma(192u, O_WH + 4 * bbytes(32), bbytes(32), 32, 0, idesc32, 1u);          // D1_3 += W3[:, 93:] . h2
-        else mma(224u, O_WH + (uint32_t)(l == 3 ? 6 : 2 * l) * bbytes(32), bbytes(32), 32, 0, idesc32, 0u);  // W1, W2, W4
-      });
-      // stash + the next block's feature term, under the product
-      if (valid) {
-        if (a.relu_bits) reinterpret_cast<uint16_t*>(a.relu_bits)[((int64_t)l * N + n) * 2 + half] = (uint16_t)bits;
-        if (a.H) {
-          float4* o = reinterpret_cast<float4*>(a.H + (int64_t)l * 32 * N);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) o[(int64_t)(4 * half + q) * N + n] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-        }
-      }
-      if (l < 3) {
-        float d2[16];
-        tmem_ld16(tm_lane + 32u * (l + 1) + col0, d2);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) s2[j] = d2[j] + sm[S_BC + (l + 1) * 32 + col0 + j];
-      }
-      wait_mma();
-    }
-    // ---- block 4 + output layer: half 0 finishes the whole row (32 columns)
-    if (half == 0) {
-      float d1[32], d2[32], h[32];
-      umma::tmem_ld32(tm_lane + 224u, d1);
-      umma::tmem_ld32(tm_lane + 128u, d2);
-      uint32_t bits = 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pre = d1[j] + sm[S_BIAS + 128 + j];
-        bits |= (pre > 0.f) ? (1u << j) : 0u;
-        h[j] = fmaxf(pre, 0.f) + (d2[j] + sm[S_BC + 128 + j]);
-      }
-      float out[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o) {
-        float s = sm[S_BO + o];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s = fmaf(sm[S_WO + o * 32 + j], h[j], s);
-        out[o] = s;
-      }
-      if (valid) {
-        if (a.relu_bits) a.relu_bits[(int64_t)4 * N + n] = bits;
-        if (a.H) store_planar32(a.H + (int64_t)4 * 32 * N, N, n, h);
-        float4* r = reinterpret_cast<float4*>(a.raw) + n;
-        const bool force = a.apply_mask && !sp.inside;
-        if (NOUT == 4) {
-          *r = make_float4(out[0], out[1], out[2], force ? 100.f : out[3]);
-        } else {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.out_mode != PN_OUT_SET_ALL) v = *r;
-          v.w = (a.out_mode == PN_OUT_ADD_W) ? v.w + out[0] : out[0];
-          if (force) v.w = 100.f;
-          *r = v;
-        }
-      }
-    }
-    // this tile's TMEM reads (tcgen05.wait::ld) are ordered before the next tile's MMAs by the
-    // fence + group barrier inside the next publish_and_issue
-    umma::tc_fence_before();
-  }
-  umma::tc_fence_before();
-  __syncthreads();
-  if (tid < 32) umma::tmem_dealloc(tmem_base_s, 512);
-}
-
-inline bool use_tensor_cores() {
-  const char* e = getenv("PN_MLP_ENGINE");   // "ffma" forces the exact-FP32 FFMA kernels
-  return !(e && e[0] == 'f');
-}
-
 template <int CD, int NOUT>
 int launch_fwd(const FwdArgs& a, cudaStream_t st) {
-  if (use_tensor_cores()) {
-    auto kern = k_grid_mlp_fwd_tc<CD, NOUT>;
-    const size_t sm = tc::smem_total<CD>();
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    const int64_t pairs = ((a.pts.N + 127) / 128 + 1) / 2;
-    const int grid = (int)((pairs < (int64_t)sm_count()) ? pairs : (int64_t)sm_count());
-    kern<<<grid, 512, sm, st>>>(a);
-    return launch_status("k_grid_mlp_fwd_tc");
-  }
+  if (use_tensor_cores()) return launch_fwd_tc(CD, NOUT, a, st);
   auto kern = k_grid_mlp_fwd<CD, NOUT>;
   const size_t sm = smem_bytes<CD>();
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -956,329 +576,9 @@ int launch_fwd(const FwdArgs& a, cudaStream_t st) {
   return launch_status("k_grid_mlp_fwd");
 }
 
-// ---------------------------------------------------------------------------
-// backward (input gradients) on the tensor cores
-// ---------------------------------------------------------------------------
-// Same tiling as the forward: CTA = 3 groups x 256 threads, two threads per sample row.
-// Every transposed mat-vec of the FFMA kernel becomes D[128 x N] (+)= G[128 x 32] . (W^T)[N x 32]^T
-// with the gradient operand G (hi/lo) in the group's shared buffer and the transposed weights
-// pre-split in shared memory.  Tensor-memory columns per group:
-//     0..31   D_gc = feature gradient, accumulated over blocks
-//    32..63   D_x  = ga_l . W_l                     (gradient gh_{l-1} at the previous block's output)
-//    64..159  D_ge = ga_3 . W3[:, :93] + ga_0 . W0  (gradient at the Fourier embedding)
-// One tensor-core round trip per block: the feature gradient sum_l gh_l . Wc_l is rewritten with
-// gh_{l-1} = ga_l . W_l as  go . (Wo Wc_4) + sum_{l>=1} ga_l . (W_l Wc_{l-1}),  so the SAME operand ga_l
-// feeds both products of a block (the weight products M_{l-1} = W_l Wc_{l-1} are formed once per
-// CTA while staging; the go term is four FMAs per column in registers).
-namespace tcb {
-using tc::kLbo; using tc::kASbo; using tc::kABytes;
-constexpr int kGroups = 3;                     // independent 128-sample tiles in flight per CTA (160 TMEM columns each)
-constexpr uint32_t kBB = 4096;                 // one [32 x 32] operand copy
-constexpr uint32_t kBE = 12288;                // one [96 x 32] operand copy
-constexpr uint32_t O_WT = 0;                   // W1^T, W2^T, W3h^T, W4^T (hi, lo each)
-constexpr uint32_t O_WCT = O_WT + 8 * kBB;     // M_m^T = (W_{m+1} Wc_m[:, :32])^T, m = 0..3
-constexpr uint32_t O_W0T = O_WCT + 8 * kBB;    // W0^T  [96 x 32]
-constexpr uint32_t O_W3ET = O_W0T + 2 * kBE;   // W3[:, :93]^T
-constexpr uint32_t O_A = O_W3ET + 2 * kBE;     // 2 groups x (hi, lo)
-constexpr uint32_t O_SMALL = O_A + kGroups * 2 * kABytes;
-constexpr int S_B = 0, S_WO = 288, S_WOC = 416, S_TOTAL = 544;  // floats
-constexpr uint32_t kSmem = O_SMALL + S_TOTAL * 4u + 40u;
-constexpr int kTileLd = 36;                    // padded row of the feature-gradient tile (reuses the A buffer; 16-byte aligned rows)
-
-// B operand = transpose of a row-major [32 x ld] weight block: element (n, j) = src[j*ld + col0 + n], n < nrows
-__device__ __forceinline__ void stage_bt(unsigned char* hi, uint32_t copy_bytes, const float* __restrict__ src, int ld, int col0,
-                                         int nrows, int nvalid) {
-  unsigned char* lo = hi + copy_bytes;
-  for (int i = threadIdx.x; i < nrows * 32; i += blockDim.x) {
-    const int j = i / nrows, n = i - j * nrows;   // n fastest: coalesced over the source row
-    const float w = n < nvalid ? src[j * ld + col0 + n] : 0.f;
-    float h, l;
-    umma::split_tf32(w, h, l);
-    const uint32_t off = umma::kmajor_off(n, j, kLbo, 1024u);
-    *reinterpret_cast<float*>(hi + off) = h;
-    *reinterpret_cast<float*>(lo + off) = l;
-  }
-}
-
-// B operand = transpose of the weight product M = Wl[:, colw .. colw+31] . Wc[:, :32]   ([32 x 32], FP32 sums)
-__device__ __forceinline__ void stage_prod_t(unsigned char* hi, uint32_t copy_bytes, const float* __restrict__ Wl, int ldw, int colw,
-                                             const float* __restrict__ Wc, int cd) {
-  unsigned char* lo = hi + copy_bytes;
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-    const int k = i >> 5, n = i & 31;
-    float m = 0.f;
-    for (int t = 0; t < 32; ++t) m = fmaf(Wl[k * ldw + colw + t], Wc[t * cd + n], m);
-    float h, l;
-    umma::split_tf32(m, h, l);
-    const uint32_t off = umma::kmajor_off(n, k, kLbo, 1024u);
-    *reinterpret_cast<float*>(hi + off) = h;
-    *reinterpret_cast<float*>(lo + off) = l;
-  }
-}
-}  // namespace tcb
-
-template <int CD, int NOUT, bool GRID_GRAD, bool NEED_DP, bool WS>
-__global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const BwdArgs a) {
-  extern __shared__ __align__(128) unsigned char smraw[];
-  using namespace tcb;
-  constexpr bool EMB = NEED_DP || WS;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int grp = tid >> 8, gw = (tid >> 5) & 7, quarter = gw & 3, half = gw >> 2;
-  const int row = quarter * 32 + lane, col0 = 16 * half;
-  float* sm = reinterpret_cast<float*>(smraw + O_SMALL);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S_TOTAL);
-  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 8);
-  unsigned char* a_hi = smraw + O_A + (uint32_t)grp * 2u * kABytes;
-  unsigned char* a_lo = a_hi + kABytes;
-  float* gtile = reinterpret_cast<float*>(a_hi);   // [128][36] floats, valid between the last MMA and the next tile
-  if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
-  if (tid == 0) { for (int i = 0; i < kGroups; ++i) umma::mbar_init(&bars[i], 1); umma::fence_mbar_init(); }
-  stage_bt(smraw + O_WT, kBB, a.w.W[1], 32, 0, 32, 32);
-  stage_bt(smraw + O_WT + 2 * kBB, kBB, a.w.W[2], 32, 0, 32, 32);
-  stage_bt(smraw + O_WT + 4 * kBB, kBB, a.w.W[3], PN_EMBED + 32, PN_EMBED, 32, 32);
-  stage_bt(smraw + O_WT + 6 * kBB, kBB, a.w.W[4], 32, 0, 32, 32);
-  constexpr bool GC = GRID_GRAD || NEED_DP;
-  if (GC) {
-    stage_prod_t(smraw + O_WCT, kBB, a.w.W[1], 32, 0, a.w.Wc[0], CD);
-    stage_prod_t(smraw + O_WCT + 2 * kBB, kBB, a.w.W[2], 32, 0, a.w.Wc[1], CD);
-    stage_prod_t(smraw + O_WCT + 4 * kBB, kBB, a.w.W[3], PN_EMBED + 32, PN_EMBED, a.w.Wc[2], CD);
-    stage_prod_t(smraw + O_WCT + 6 * kBB, kBB, a.w.W[4], 32, 0, a.w.Wc[3], CD);
-    for (int i = tid; i < 128; i += blockDim.x) {   // (Wo Wc_4)[o][j]
-      const int o = i >> 5, j = i & 31;
-      float m = 0.f;
-      if (o < NOUT)
-        for (int t = 0; t < 32; ++t) m = fmaf(a.w.Wo[o * 32 + t], a.w.Wc[4][t * CD + j], m);
-      sm[S_WOC + i] = m;
-    }
-  }
-  if (EMB) {
-    stage_bt(smraw + O_W0T, kBE, a.w.W[0], PN_EMBED, 0, 96, PN_EMBED);
-    stage_bt(smraw + O_W3ET, kBE, a.w.W[3], PN_EMBED + 32, 0, 96, PN_EMBED);
-  }
-  for (int i = tid; i < 288; i += blockDim.x) { const int d = i / 96, k = i % 96; sm[S_B + i] = k < PN_EMBED ? a.w.B[d * PN_EMBED + k] : 0.f; }
-  for (int i = tid; i < 128; i += blockDim.x) sm[S_WO + i] = i < NOUT * 32 ? a.w.Wo[i] : 0.f;
-  umma::fence_proxy_async();
-  umma::tc_fence_before();
-  __syncthreads();
-  umma::tc_fence_after();
-  const uint32_t tm = tmem_base_s + (uint32_t)grp * 160u;
-  const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);
-  const uint32_t sA = umma::smem_u32(a_hi), sW = umma::smem_u32(smraw);
-  constexpr uint32_t idesc32 = umma::instr_desc_tf32(128, 32), idesc96 = umma::instr_desc_tf32(128, 96);
-  uint64_t* bar = &bars[grp];
-  uint32_t phase = 0;
-  const bool issuer = (tid & 255) == 0;
-  const uint64_t dA_hi = umma::smem_desc(sA, kLbo, kASbo), dA_lo = umma::smem_desc(sA + kABytes, kLbo, kASbo);
-  constexpr uint32_t kStep = (2u * kLbo) >> 4;
-  auto mma = [&](uint32_t dcol, uint32_t boff, uint32_t copy_bytes, uint32_t idesc, uint32_t acc) {
-    const uint64_t dB_hi = umma::smem_desc(sW + boff, kLbo, 1024u), dB_lo = umma::smem_desc(sW + boff + copy_bytes, kLbo, 1024u);
-    umma::mma_3xtf32_k32(tm + dcol, dA_hi, dA_lo, dB_hi, dB_lo, kStep, kStep, idesc, acc);
-  };
-  auto group_bar = [&] { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); };
-  auto publish_issue = [&](auto&& issue) {
-    umma::fence_proxy_async();
-    umma::tc_fence_before();
-    group_bar();
-    if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
-  };
-  auto wait_mma = [&] {   // one lane polls the mbarrier; the rest of the group sleeps on a named barrier
-    if ((tid & 255) < 32) { if (lane == 0) umma::mbar_wait(bar, phase); __syncwarp(); }
-    asm volatile("bar.sync %0, 256;" ::"r"(grp + 4) : "memory");
-    phase ^= 1u;
-    umma::tc_fence_after();
-  };
-  auto store_half_row = [&](const float (&v)[16]) {
-    const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)(4 * half) * kLbo;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 h, l;
-      umma::split_tf32(v[4 * q], h.x, l.x); umma::split_tf32(v[4 * q + 1], h.y, l.y);
-      umma::split_tf32(v[4 * q + 2], h.z, l.z); umma::split_tf32(v[4 * q + 3], h.w, l.w);
-      *reinterpret_cast<float4*>(a_hi + base + q * kLbo) = h;
-      *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
-    }
-  };
-  auto stash_half = [&](float* base, int64_t N, int64_t n, const float (&v)[16]) {
-    float4* o = reinterpret_cast<float4*>(base);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o[(int64_t)(4 * half + q) * N + n] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  };
-
-  const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
-  for (int64_t t = (int64_t)blockIdx.x * kGroups + grp; t < ntiles; t += (int64_t)gridDim.x * kGroups) {
-    const int64_t n = t * 128 + row;
-    const bool valid = n < N;
-    Sample sp;
-    sp.pf[0] = sp.pf[1] = sp.pf[2] = 0.f; sp.xn[0] = sp.xn[1] = sp.xn[2] = 0.f; sp.inside = true;
-    if (valid) load_sample(a.pts, n, a.nb, a.mb, sp);
-    const unsigned vm = __ballot_sync(kFull, valid);
-    float go[4] = {0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-      const float4 g = reinterpret_cast<const float4*>(a.g_raw)[n];
-      if (NOUT == 4) { go[0] = g.x; go[1] = g.y; go[2] = g.z; }
-      else go[0] = (a.apply_mask && !sp.inside) ? 0.f : g.w;
-    }
-    if (WS && valid && half == 0) {
-      reinterpret_cast<float4*>(a.GO)[n] = make_float4(go[0], go[1], go[2], go[3]);
-      a.P32[n] = sp.pf[0]; a.P32[N + n] = sp.pf[1]; a.P32[2 * N + n] = sp.pf[2];
-    }
-    float gh[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o) s = fmaf(sm[S_WO + o * 32 + col0 + j], go[o], s);
-      gh[j] = s;
-    }
-    // the previous tile's scatter phase used the A buffer as a scratch tile: all of the group must be done with it
-    group_bar();
-    uint32_t bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)4 * N + n) * 2 + half] : 0u;
-#pragma unroll 1
-    for (int l = 4; l >= 0; --l) {
-      if (WS && valid) stash_half(a.GH + (int64_t)l * 32 * N, N, n, gh);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) gh[j] = ((bits >> j) & 1u) ? gh[j] : 0.f;    // ga_l
-      if (l > 0 || EMB) {
-        store_half_row(gh);
-        publish_issue([&] {
-          if (l == 4) mma(32u, O_WT + 6 * kBB, kBB, idesc32, 0u);
-          else if (l == 3) { mma(32u, O_WT + 4 * kBB, kBB, idesc32, 0u); if (EMB) mma(64u, O_W3ET, kBE, idesc96, 0u); }
-          else if (l == 2) mma(32u, O_WT + 2 * kBB, kBB, idesc32, 0u);
-          else if (l == 1) mma(32u, O_WT, kBB, idesc32, 0u);
-          else mma(64u, O_W0T, kBE, idesc96, 1u);
-          if (GC && l > 0) mma(0u, O_WCT + (uint32_t)(l - 1) * 2u * kBB, kBB, idesc32, l < 4 ? 1u : 0u);   // D_gc (+)= ga_l . M_{l-1}
-        });
-      }
-      // under the products: stash, next block's ReLU bits
-      if (WS && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);
-      if (l > 0) bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)(l - 1) * N + n) * 2 + half] : 0u;
-      if (l > 0 || EMB) {
-        wait_mma();
-        if (l > 0) tmem_ld16(tm_lane + 32u + col0, gh);
-      }
-    }
-    // ---- Fourier embedding: gradient at the arguments, point gradient, dB scratch
-    float gp[3] = {0.f, 0.f, 0.f};
-    if (EMB) {
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        float ge[16];
-        tmem_ld16(tm_lane + 64u + 32u * c + col0, ge);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int kk = 32 * c + col0 + k;
-          const float bx = sm[S_B + kk], by = sm[S_B + 96 + kk], bz = sm[S_B + 192 + kk];
-          const float garg = ge[k] * fourier_cos(fmaf(sp.pf[2], bz, fmaf(sp.pf[1], by, sp.pf[0] * bx)));
-          ge[k] = garg;
-          gp[0] = fmaf(bx, garg, gp[0]); gp[1] = fmaf(by, garg, gp[1]); gp[2] = fmaf(bz, garg, gp[2]);
-        }
-        if (WS && valid) {
-          float4* o = reinterpret_cast<float4*>(a.GARG);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            o[(int64_t)(8 * c + 4 * half + q) * N + n] = make_float4(ge[4 * q], ge[4 * q + 1], ge[4 * q + 2], ge[4 * q + 3]);
-        }
-      }
-    }
-    // ---- feature gradient: TMEM -> scratch tile [row][channel] -> warp-cooperative scatter
-    if (GRID_GRAD || NEED_DP) {
-      float gc[16];
-      tmem_ld16(tm_lane + col0, gc);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) gc[j] = fmaf(sm[S_WOC + o * 32 + col0 + j], go[o], gc[j]);   // gh_4 . Wc_4
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(gtile + row * kTileLd + col0 + 4 * q) = make_float4(gc[4 * q], gc[4 * q + 1], gc[4 * q + 2], gc[4 * q + 3]);
-      umma::tc_fence_before();
-      group_bar();
-      // warp (quarter, half) scatters rows 32*quarter + 16*half + [0,16): 8 lanes per sample (lane&7 = channel
-      // quad, 128-bit vector reductions), 4 samples per iteration
-      const GridDev& g = a.ga;
-      const float ux = unnormalise(sp.xn[0], g.W), uy = unnormalise(sp.xn[1], g.H), uz = unnormalise(sp.xn[2], g.D);
-      const int q = lane & 7, sub = lane >> 3;
-      float dux = 0.f, duy = 0.f, duz = 0.f;
-#pragma unroll 1
-      for (int it = 0; it < 4; ++it) {
-        const int src = 16 * half + 4 * it + sub;
-        const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        if ((vm >> src) & 1u) {
-          const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
-          const float4 gv = *reinterpret_cast<const float4*>(gtile + (quarter * 32 + src) * kTileLd + 4 * q);
-          if (GRID_GRAD) {
-            float* gg = a.g_grid + c.base + 4 * q;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if ((c.ok >> k) & 1u) {
-                const float w = corner_weight(c, k);
-                red_add_v4(gg + corner_offset(k, g.W, g.H), w * gv.x, w * gv.y, w * gv.z, w * gv.w);
-              }
-            }
-          }
-          if (NEED_DP) {
-            const float4* gd = reinterpret_cast<const float4*>(g.data + c.base) + q;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if ((c.ok >> k) & 1u) {
-                const float4 f = __ldg(gd + corner_offset(k, g.W, g.H) / 4);
-                const float v = fmaf(f.w, gv.w, fmaf(f.z, gv.z, fmaf(f.y, gv.y, f.x * gv.x)));
-                const float wx = c.wx[k & 1], wy = c.wy[(k >> 1) & 1], wz = c.wz[k >> 2];
-                gx += ((k & 1) ? v : -v) * wy * wz;
-                gy += (((k >> 1) & 1) ? v : -v) * wx * wz;
-                gz += ((k >> 2) ? v : -v) * wx * wy;
-              }
-            }
-            gx *= c.gm[0]; gy *= c.gm[1]; gz *= c.gm[2];
-          }
-        }
-        if (NEED_DP) {
-          // sum over the sample's 8 lanes, then hand the result to the lane that owns the row
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) {
-            gx += __shfl_xor_sync(kFull, gx, o); gy += __shfl_xor_sync(kFull, gy, o); gz += __shfl_xor_sync(kFull, gz, o);
-          }
-          const int from = 8 * (lane & 3);
-          const float rx = __shfl_sync(kFull, gx, from), ry = __shfl_sync(kFull, gy, from), rz = __shfl_sync(kFull, gz, from);
-          if (lane == 16 * half + 4 * it + (lane & 3)) { dux = rx; duy = ry; duz = rz; }
-        }
-      }
-      if (NEED_DP) {
-        // rows 16*half..16*half+15 of this quarter got their grid-path gradient in lanes 16*half + i of THIS warp;
-        // combine with the embedding path: each (row, half) thread holds gp of its own 16 embedding columns
-        const bool mine = (lane >> 4) == half;   // this lane's row was scattered by this warp
-        if (mine && valid) {
-          gp[0] += norm_grad(a.pts, a.nb, 0, dux); gp[1] += norm_grad(a.pts, a.nb, 1, duy); gp[2] += norm_grad(a.pts, a.nb, 2, duz);
-        }
-        if (valid) {
-          // each (row, half) thread adds its partial sum; float atomics on 3 words per row, 2 adders per word
-          float* o = a.g_pts + 3 * n;
-          atomicAdd(o, gp[0]); atomicAdd(o + 1, gp[1]); atomicAdd(o + 2, gp[2]);
-        }
-      }
-    } else if (NEED_DP && valid) {
-      float* o = a.g_pts + 3 * n;
-      atomicAdd(o, gp[0]); atomicAdd(o + 1, gp[1]); atomicAdd(o + 2, gp[2]);
-    }
-    umma::tc_fence_before();
-  }
-  umma::tc_fence_before();
-  __syncthreads();
-  if (tid < 32) umma::tmem_dealloc(tmem_base_s, 512);
-}
-
 template <int CD, int NOUT, bool GG, bool DP, bool WS>
 int launch_bwd_t(const BwdArgs& a, cudaStream_t st) {
-  if (use_tensor_cores()) {
-    auto kern = k_grid_mlp_bwd_tc<CD, NOUT, GG, DP, WS>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmem);
-    const int64_t pairs = ((a.pts.N + 127) / 128 + tcb::kGroups - 1) / tcb::kGroups;
-    const int grid = (int)((pairs < (int64_t)sm_count()) ? pairs : (int64_t)sm_count());
-    kern<<<grid, tcb::kGroups * 256, tcb::kSmem, st>>>(a);
-    return launch_status("k_grid_mlp_bwd_tc");
-  }
+  if (use_tensor_cores()) return launch_bwd_tc(CD, NOUT, GG, DP, WS, a, st);
   auto kern = k_grid_mlp_bwd<CD, NOUT, GG, DP, WS>;
   const size_t sm = (size_t)(wfloats<CD>() + 32 * kLdc) * sizeof(float);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

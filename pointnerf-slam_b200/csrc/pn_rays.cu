@@ -218,6 +218,22 @@ __global__ void __launch_bounds__(128) k_ray_zvals(const float* __restrict__ ro,
         z[ns + k] = __dadd_rn(__dmul_rn(0.001, __dsub_rn(1.0, ts[k])), __dmul_rn((double)dmax, ts[k]));
     }
     S = ns + nsurf;
+    // torch.sort of the concatenation (Renderer.py:157).  Both runs are normally ascending already
+    // (t_vals / t_surface increase, far >= near), so a merge gives the sorted row in S steps; a
+    // descending run (far < near: the ray leaves the box at once) falls back to the general sort.
+    bool ascending = true;
+    for (int k = 1; k < ns; ++k) ascending = ascending && (z[k - 1] <= z[k]);
+    for (int k = ns + 1; k < S; ++k) ascending = ascending && (z[k - 1] <= z[k]);
+    if (ascending) {
+      int i = 0, j = ns;
+      double a = z[0], c = z[ns];
+      for (int k = 0; k < S; ++k) {
+        const bool take_a = (j >= S) || (i < ns && a <= c);
+        zout[r * S + k] = take_a ? a : c;
+        if (take_a) { ++i; a = i < ns ? z[i] : a; } else { ++j; c = j < S ? z[j] : c; }
+      }
+      return;
+    }
     insertion_sort(z, S);
   }
   for (int k = 0; k < S; ++k) zout[r * S + k] = z[k];
