@@ -17,9 +17,9 @@
 //     A_C = [c(CD)|0]       x [GH_0..GH_4]          (N = 160) -> dWc_0..4
 // 11 FP32 accumulators (352 tensor-memory columns) stay resident for the whole kernel; each CTA
 // flushes them once with atomics.  Two operand stages alternate: while the tensor core works on
-// chunk i, the 512 threads split / transpose chunk i+1 (an mbarrier per stage, armed by
-// tcgen05.commit, says when a stage may be overwritten), and the global loads of chunk i+2 are
-// already in flight in registers.  Bias gradients (column sums of GA_l /
+// chunk i, the 512 threads load / split / transpose chunk i+1 (an mbarrier per stage, armed by
+// tcgen05.commit, says when a stage may be overwritten); chunks i+2.. are on their way into L2
+// (prefetch.global.L2).  Bias gradients (column sums of GA_l /
 // GH_l) are accumulated by the loading threads on the side.
 #include "pn_common.cuh"
 #include "pn_umma.cuh"
@@ -111,44 +111,57 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgTcArgs a) {
   const float4* GA4 = reinterpret_cast<const float4*>(a.GA);
   const float4* GH4 = reinterpret_cast<const float4*>(a.GH);
   const int64_t nchunks = (N + kChunk - 1) / kChunk;
-  // this thread's share of one chunk: up to six 16-byte loads (coalesced 256-byte rows per half-warp)
-  struct Regs { float4 vh, ve, vc, vg[3]; };
-  auto load_chunk = [&](int64_t c, Regs& r) {
+  // this thread's share of one chunk: up to six 16-byte loads (coalesced 256-byte rows per half-warp).
+  // The rows of a chunk lie megabytes apart, so their DRAM latency is what a lock-step iteration would
+  // wait for; an L2 prefetch three chunks ahead (no register, no scoreboard, not ordered by the proxy
+  // fence below) turns those loads into L2 hits.
+  auto prefetch_chunk = [&](int64_t c) {
     const int64_t n = c * kChunk + s;
-    const bool ok = c < nchunks && n < N;
-    r.vh = ok ? H4[(int64_t)slot * N + n] : z4;                       // [h0|h1|h2|h3]: quad = slot
-    r.ve = (ok && slot < 24) ? E4[(int64_t)slot * N + n] : z4;
-    r.vc = (ok && slot < cq) ? C4[(int64_t)slot * N + n] : z4;
+    if (c >= nchunks || n >= N) return;
+    auto pf = [](const float4* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+    pf(H4 + (int64_t)slot * N + n);
+    if (slot < 24) pf(E4 + (int64_t)slot * N + n);
+    if (slot < cq) pf(C4 + (int64_t)slot * N + n);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int row = i * 32 + slot;             // 0..79: GA_0..4 (rows 0..39), GH_0..4 (40..79)
-      r.vg[i] = z4;
-      if (ok && row < 80) r.vg[i] = row < 40 ? GA4[(int64_t)row * N + n] : GH4[(int64_t)(row - 40) * N + n];
+      const int row = i * 32 + slot;
+      if (row < 80) pf(row < 40 ? GA4 + (int64_t)row * N + n : GH4 + (int64_t)(row - 40) * N + n);
     }
   };
+  constexpr int kAhead = 3;
+  for (int d = 1; d < kAhead; ++d) prefetch_chunk(blockIdx.x + (int64_t)d * gridDim.x);
   int it = 0;
-  Regs cur, nxt;
-  load_chunk(blockIdx.x, cur);
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
     const int st = it & 1;
     unsigned char* base = smraw + st * kStage;
-    // the next chunk's global loads are in flight while this chunk is split, transposed and multiplied
-    load_chunk(c + gridDim.x, nxt);
+    const int64_t n = c * kChunk + s;
+    const bool ok = n < N;
+    prefetch_chunk(c + (int64_t)kAhead * gridDim.x);
+    // global loads first (they do not touch shared memory), then wait for the stage to be free
+    const float4 vh = ok ? H4[(int64_t)slot * N + n] : z4;                       // [h0|h1|h2|h3]: quad = slot
+    const float4 ve = (ok && slot < 24) ? E4[(int64_t)slot * N + n] : z4;
+    const float4 vc = (ok && slot < cq) ? C4[(int64_t)slot * N + n] : z4;
+    float4 vg[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int row = r * 32 + slot;             // 0..79: GA_0..4 (rows 0..39), GH_0..4 (40..79)
+      vg[r] = z4;
+      if (ok && row < 80) vg[r] = row < 40 ? GA4[(int64_t)row * N + n] : GH4[(int64_t)(row - 40) * N + n];
+    }
     if (it >= 2) { umma::mbar_wait(&bars[st], phase[st]); phase[st] ^= 1u; umma::tc_fence_after(); }
-    put_split(base + O_AH, kACopy, slot, s, cur.vh);
-    if (slot < 24) put_split(base + O_AE, kACopy, slot, s, cur.ve);
-    if (slot < cq) put_split(base + O_AC, kACopy, slot, s, cur.vc);
+    put_split(base + O_AH, kACopy, slot, s, vh);
+    if (slot < 24) put_split(base + O_AE, kACopy, slot, s, ve);
+    if (slot < cq) put_split(base + O_AC, kACopy, slot, s, vc);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int row = r * 32 + slot;
       if (row < 80) {
         const int arr = row >> 3;                                        // GA_l = l, GH_l = 5 + l
         const int pos = arr == 1 ? 2 : arr == 2 ? 3 : arr == 3 ? 1 : arr;  // position in shared memory
-        put_split(base + O_B + (uint32_t)pos * kBCopy, kBLo, row & 7, s, cur.vg[r]);
-        bsum[r].x += cur.vg[r].x; bsum[r].y += cur.vg[r].y; bsum[r].z += cur.vg[r].z; bsum[r].w += cur.vg[r].w;
+        put_split(base + O_B + (uint32_t)pos * kBCopy, kBLo, row & 7, s, vg[r]);
+        bsum[r].x += vg[r].x; bsum[r].y += vg[r].y; bsum[r].z += vg[r].z; bsum[r].w += vg[r].w;
       }
     }
-    cur = nxt;
     umma::fence_proxy_async();
     umma::tc_fence_before();
     __syncthreads();
