@@ -157,7 +157,10 @@ def run_ours(args):
         n_arena = sum(g.numel() for k, g in grids.items() if k != "grid_coarse") + 65536
         arena = E.GradArena(n_arena, dev)
         E.GRAD_ARENA = arena
-    reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "arena") == "arena" else None)
+    reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "arena" else None)
+    comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "0"))
+    if world > 1 and comm_sms > 0:   # leave SMs free so that NCCL kernels can run beside the persistent decoder kernels
+        L.lib().pn_reserve_sms(comm_sms)
 
     def h2d_inputs():   # host -> device copy of this step's inputs from pinned memory (e2e only)
         frames[0][0].copy_(pinned_depth, non_blocking=True)
@@ -180,7 +183,7 @@ def run_ours(args):
         # Mapper.py:641-646 (masked L1 depth + weighted L1 colour), written without boolean indexing so that
         # the host does not synchronise in the middle of the step
         loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
-        if world > 1 and os.environ.get("PN_BENCH_ALLREDUCE", "arena") == "simple":
+        if world > 1 and os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "simple":
             loss.backward()
             D.allreduce_gradients([t.grad for t in trained])
         elif world > 1:   # one all-reduce over the gradient arena (or per-gradient overlapped reductions)
@@ -346,7 +349,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.light:
         line["cpu_baseline"] = cpu_baseline(sample_kf_pixels=200, iters=2)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     # Teardown.  A captured graph that contains NCCL kernels must be released before the process group
     # goes away, and no rank may sit in a collective at exit: drop the graph, synchronise, and leave
     # through os._exit (skipping NCCL's destructor-time rendezvous, which can wait forever on a
@@ -443,7 +446,20 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": round(value, 1), "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any library prints
+    (NCCL's version banner, warnings) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -455,6 +471,10 @@ def main():
     ap.add_argument("--light", action="store_true", help="profiling runs: skip the e2e pass and the CPU baseline")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)     # keep stdout for the JSON line only
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

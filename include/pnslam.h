@@ -118,6 +118,11 @@ const char* pn_last_error(void);
 int pn_version(void);
 /* number of kernels this process has launched through the library (for bench accounting) */
 long long pn_launch_count(void);
+/* The decoder kernels are persistent, one CTA per SM with nearly all of its shared memory, so a kernel
+ * of another stream (an NCCL all-reduce of finished gradients) cannot start beside them.  Reserving n
+ * SMs makes every later launch size its grid for (SM count - n); returns the previous value.
+ * No reference counterpart (the reference is single-GPU); used by the data-parallel mapper. */
+int pn_reserve_sms(int n);
 
 /* -------- pose and ray generation (src/common.py:74-176, 248-266) -------- */
 
