@@ -150,13 +150,12 @@ def run_ours(args):
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    # N > 1: every gradient sink of the backward comes from one arena -> one memset, one all-reduce
+    # every gradient sink of the backward comes from one arena -> one memset per iteration instead of ~20
+    # small fills (and, on several GPUs, the option of ONE all-reduce over it)
     from pointnerf_slam_b200 import engine as E
-    arena = None
-    if world > 1:
-        n_arena = sum(g.numel() for k, g in grids.items() if k != "grid_coarse") + 65536
-        arena = E.GradArena(n_arena, dev)
-        E.GRAD_ARENA = arena
+    n_arena = sum(g.numel() for k, g in grids.items() if k != "grid_coarse") + N_KEYFRAMES * PIX_PER_KF * S * 3 + 262144
+    arena = E.GradArena(n_arena, dev)
+    E.GRAD_ARENA = arena
     reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "arena" else None)
     comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "0"))
     if world > 1 and comm_sms > 0:   # leave SMs free so that NCCL kernels can run beside the persistent decoder kernels
@@ -184,6 +183,7 @@ def run_ours(args):
         # the host does not synchronise in the middle of the step
         loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
         if world > 1 and os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "simple":
+            arena.reset()
             loss.backward()
             D.allreduce_gradients([t.grad for t in trained])
         elif world > 1:   # one all-reduce over the gradient arena (or per-gradient overlapped reductions)
@@ -193,6 +193,7 @@ def run_ours(args):
             reducer.finish({k: grids[k] for k in ("grid_middle", "grid_fine", "grid_color")},
                            decoders={"color": model.color_decoder}, others=[c.grad for c in cams[1:]])
         else:
+            arena.reset()
             loss.backward()
         return loss
 
@@ -210,27 +211,15 @@ def run_ours(args):
     graph = {"g": None, "loss": None, "launches": 0}
 
     def capture():
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                eager_step(False)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        g.register_generator_state(gen)
-        n0 = L.lib().pn_launch_count()
-        with torch.cuda.graph(g):
-            graph["loss"] = step_body()
-        graph["launches"] = L.lib().pn_launch_count() - n0
-        graph["g"] = g
+        gs = P.graphs.GraphedStep(step_body, generators=[gen], warmup=3)
+        graph["g"], graph["loss"], graph["launches"] = gs, gs.out, gs.launches
 
     def step(e2e=False):
         if graph["g"] is None:
             return eager_step(e2e)
         if e2e:
             h2d_inputs()
-        graph["g"].replay()
+        graph["g"]()
         return graph["loss"].item() if e2e else None
 
     def timed(k, e2e, profile):
@@ -357,6 +346,8 @@ def run_ours(args):
     watchdog = threading.Timer(60.0, lambda: os._exit(0))   # never outlive the measurement by more than a minute
     watchdog.daemon = True
     watchdog.start()
+    if graph["g"] is not None:
+        graph["g"].release()
     graph["g"] = None
     graph["loss"] = None
     torch.cuda.synchronize()

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import engine as E
 
 f32 = C.c_float
 
@@ -129,7 +130,7 @@ class _SampleRaysFn(torch.autograd.Function):
         H0, W0, Wc, W, fx, fy, cx, cy = ctx.geom
         idx = ctx.idx
         dev = idx.device
-        g = torch.zeros((3, 4), dtype=torch.float32, device=dev)
+        g = E.zeros((3, 4), dev)
         g_ro = g_ro.float().contiguous() if g_ro is not None else None
         g_rd = g_rd.float().contiguous() if g_rd is not None else None
         with L.device_guard(dev):
@@ -181,7 +182,7 @@ class _ImageRaysFn(torch.autograd.Function):
     def backward(ctx, g_ro, g_rd):
         H, W, fx, fy, cx, cy = ctx.geom
         dev = (g_ro if g_ro is not None else g_rd).device
-        g = torch.zeros((3, 4), dtype=torch.float32, device=dev)
+        g = E.zeros((3, 4), dev)
         g_ro = g_ro.float().contiguous() if g_ro is not None else None
         g_rd = g_rd.float().contiguous() if g_rd is not None else None
         with L.device_guard(dev):

@@ -100,9 +100,11 @@ __device__ __forceinline__ float norm_grad(const pn_points& ps, const Bound6& nb
   return (float)__ddiv_rn(__dmul_rn((double)g, 2.0), __dsub_rn(nb.v[2 * a + 1], nb.v[2 * a]));
 }
 
-// grid_sampler_unnormalize(align_corners=True): ((x+1)/2)*(size-1), float32.
+// grid_sampler_unnormalize(align_corners=True): ((x+1)/2)*(size-1), float32.  The division by two is
+// written as a multiplication by 0.5: exact either way, so the result is bit-identical, without the
+// IEEE division sequence.
 __device__ __forceinline__ float unnormalise(float xn, int size) {
-  return __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f), (float)(size - 1));
+  return __fmul_rn(__fmul_rn(__fadd_rn(xn, 1.0f), 0.5f), (float)(size - 1));
 }
 
 // One trilinear cell in ATen's corner order (tnw,tne,tsw,tse,bnw,bne,bsw,bse):

@@ -180,10 +180,18 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
     }
     // the previous tile's scatter phase used the A buffer as a scratch tile: all of the group must be done with it
     group_bar();
-    uint32_t bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)4 * N + n) * 2 + half] : 0u;
+    // ReLU masks of the five blocks: five independent loads in flight now, consumed block by block
+    uint32_t b01 = 0u, b23 = 0u, b4 = 0u;
+    if (valid) {
+      const uint16_t* rb = reinterpret_cast<const uint16_t*>(a.relu_bits) + 2 * n + half;
+      const uint32_t m0 = rb[0], m1 = rb[2 * N], m2 = rb[4 * N], m3 = rb[6 * N];
+      b4 = rb[8 * N];
+      b01 = m0 | (m1 << 16); b23 = m2 | (m3 << 16);
+    }
 #pragma unroll 1
     for (int l = 4; l >= 0; --l) {
       if (WS && valid) stash_half(a.GH + (int64_t)l * 32 * N, N, n, gh);
+      const uint32_t bits = l == 4 ? b4 : (l >= 2 ? b23 >> (16 * (l - 2)) : b01 >> (16 * l));
 #pragma unroll
       for (int j = 0; j < 16; ++j) gh[j] = ((bits >> j) & 1u) ? gh[j] : 0.f;    // ga_l
       if (l > 0 || EMB) {
@@ -197,9 +205,7 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
           if (GC && l > 0) mma(0u, O_WCT + (uint32_t)(l - 1) * 2u * kBB, kBB, idesc32, l < 4 ? 1u : 0u);   // D_gc (+)= ga_l . M_{l-1}
         });
       }
-      // under the products: stash, next block's ReLU bits
-      if (WS && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);
-      if (l > 0) bits = valid ? (uint32_t)reinterpret_cast<const uint16_t*>(a.relu_bits)[((int64_t)(l - 1) * N + n) * 2 + half] : 0u;
+      if (WS && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);   // under the products
       if (l > 0 || EMB) {
         wait_mma();
         if (l > 0) tmem_ld16(tm_lane + 32u + col0, gh);

@@ -65,10 +65,10 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
     asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
     if (issuer) { umma::tc_fence_after(); issue(); umma::mma_commit(bar); }
   };
-  // one lane polls the mbarrier; the other 255 threads of the group sleep on a named barrier
+  // one lane of every warp polls the mbarrier (try_wait suspends the lane between polls)
   auto wait_mma = [&] {
-    if ((tid & 255) < 32) { if (lane == 0) umma::mbar_wait(bar, phase); __syncwarp(); }
-    asm volatile("bar.sync %0, 256;" ::"r"(grp + 4) : "memory");
+    if (lane == 0) umma::mbar_wait(bar, phase);   // one polling lane per warp
+    __syncwarp();
     phase ^= 1u;
     umma::tc_fence_after();
   };

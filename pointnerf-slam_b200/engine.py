@@ -214,6 +214,14 @@ def _zeros(numel: int, device) -> torch.Tensor:
     return torch.zeros(int(numel), dtype=torch.float32, device=device)
 
 
+def zeros(shape, device) -> torch.Tensor:
+    """Zeroed float32 gradient sink of the given shape (from the arena when one is installed)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return _zeros(n, device).view(*shape)
+
+
 def new_grid_grad(g: torch.Tensor) -> torch.Tensor:
     """Zeroed gradient buffer shaped like g with channels-last memory."""
     n = g.shape[2] * g.shape[3] * g.shape[4] * 32
@@ -340,7 +348,7 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
     lib = L.lib()
     n = pts.n
     g_grids: Dict[str, torch.Tensor] = {k: new_grid_grad(grids_cl[k]) for k in plan.grid_keys if need_grid.get(k)}
-    g_pts = torch.zeros((n, 3), dtype=torch.float32, device=device) if need_pts else None
+    g_pts = zeros((n, 3), device) if need_pts else None
     g_params: List[Optional[List[torch.Tensor]]] = []
     if n == 0:
         for i, p in enumerate(plan.passes):

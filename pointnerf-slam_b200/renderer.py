@@ -142,7 +142,7 @@ class RenderRaysFn(torch.autograd.Function):
         gv = g_var.double().contiguous() if g_var is not None else None
         gc = g_rgb.float().contiguous() if g_rgb is not None else None
         g_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
-        g_rd_extra = torch.zeros((R, 3), dtype=torch.float32, device=dev) if (need_rays and not cfg.occupancy) else None
+        g_rd_extra = E.zeros((R, 3), dev) if (need_rays and not cfg.occupancy) else None
         with L.device_guard(dev):
             L.check(lib.pn_composite_bwd(C.c_void_p(ctx.raw.data_ptr()), C.c_void_p(z.data_ptr()), C.c_void_p(rd.data_ptr()),
                                          C.c_int64(R), S, int(cfg.occupancy), C.c_void_p(L.ptr(gd)), C.c_void_p(L.ptr(gv)),

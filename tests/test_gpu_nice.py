@@ -246,3 +246,40 @@ def test_composite_standalone_matches_oracle(g):
         torch.testing.assert_close(c2.cpu(), c.detach(), rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(w2.cpu(), w.detach(), rtol=1e-4, atol=1e-7)
         assert T.rel_max(rc.grad, rr.grad) < 1e-4
+
+
+def test_graphed_step_replays_the_eager_iteration():
+    """graphs.GraphedStep: a captured tracking iteration gives the eager loss and pose gradient for the same pixels."""
+    import pointnerf_slam_b200 as P
+    d = T.load_nice()
+    model, grids, renderer = T.cuda_nice(d)
+    dev = torch.device("cuda", 0)
+    renderer.freeze_map = True
+    Hh, Ww = 60, 80
+    depth = (1.0 + torch.rand(Hh, Ww, generator=torch.Generator().manual_seed(3))).to(dev)
+    color = torch.rand(Hh, Ww, 3, generator=torch.Generator().manual_seed(4)).to(dev)
+    c2w = torch.eye(4)[:3].clone()
+    c2w[:, 3] = torch.tensor([0.1, 0.2, -0.1])
+    cam = P.get_tensor_from_camera(c2w).to(dev).requires_grad_(True)
+    idx = torch.randint(Hh * Ww, (200,), generator=torch.Generator().manual_seed(5)).to(dev)
+
+    def iteration():
+        c = P.get_camera_from_tensor(cam)
+        o, dr, gd, gc = P.get_samples(0, Hh, 0, Ww, 200, Hh, Ww, 70.0, 70.0, 39.5, 29.5, c, depth, color, dev, indices=idx)
+        dd, vv, cc = renderer.render_batch_ray(grids, model, dr, o, dev, "color", gt_depth=gd)
+        loss = torch.abs(gd - dd).sum() + 0.5 * torch.abs(gc - cc).sum()
+        cam.grad = None
+        loss.backward()
+        return loss
+
+    ref_loss = iteration().item()
+    ref_grad = cam.grad.clone()
+    step = P.graphs.GraphedStep(iteration)
+    assert step.launches > 5
+    for _ in range(2):
+        out = step()
+    torch.cuda.synchronize()
+    assert abs(out.item() - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-9
+    torch.testing.assert_close(cam.grad, ref_grad, rtol=1e-4, atol=1e-7)
+    step.release()
+    renderer.freeze_map = False

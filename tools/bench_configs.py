@@ -45,6 +45,22 @@ def tracking():
     loss.backward(); cam.grad = None
 ms = timeit(tracking, 50)
 out["tracking_1000px_fwd_bwd_pose"] = {"ms_per_iter": round(ms, 4), "rays_per_s": round(1000 / ms * 1e3, 1)}
+# the same iteration captured once in a CUDA graph (the pose gradient stays in cam.grad between replays)
+def tracking_keep_grad():
+    c = P.get_camera_from_tensor(cam)
+    o, d, gd, gc = P.get_samples(100, B.H - 100, 100, B.W - 100, 1000, B.H, B.W, B.FX, B.FY, B.CX, B.CY, c, depth, color, dev)
+    dd, vv, cc = r.render_batch_ray(grids, model, d, o, dev, "color", gt_depth=gd)
+    m = gd > 0
+    loss = torch.where(m, torch.abs(gd - dd) / torch.sqrt(vv.detach() + 1e-10), torch.zeros_like(dd)).sum() + \
+        0.5 * (torch.abs(gc - cc) * m[:, None]).sum()
+    cam.grad = None
+    loss.backward()
+    return loss
+gstep = P.graphs.GraphedStep(tracking_keep_grad)
+ms = timeit(gstep, 50)
+out["tracking_1000px_fwd_bwd_pose_cuda_graph"] = {"ms_per_iter": round(ms, 4), "rays_per_s": round(1000 / ms * 1e3, 1),
+                                                   "library_kernels_per_replay": gstep.launches}
+gstep.release()
 r.freeze_map = False
 
 # ---- [5a] dense render
