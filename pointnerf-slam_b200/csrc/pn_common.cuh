@@ -27,6 +27,10 @@ int sm_count();
 // tensor-core weight gradients (pn_wgrad_tc.cu): 0 ok, 1 error, -1 not applicable
 int launch_wgrad_tc(int64_t N, int c_dim, const float* H, const float* C, const float* E, const float* GA, const float* GH,
                     float* const* W, float* const* b, float* const* Wc, float* const* bc, cudaStream_t st);
+// c_dim 32: all parameter gradients in one kernel; GA is rebuilt from GH and the forward's ReLU bits
+int launch_wgrad_tc32(int64_t N, int n_out, const float* H, const float* C, const float* E, const float* GH, const float* GARG,
+                      const float* GO, const float* P32, const uint32_t* relu_bits, float* const* W, float* const* b,
+                      float* const* Wc, float* const* bc, float* Wo, float* bo, float* B, cudaStream_t st);
 
 struct Bound6 {  // [lo_x hi_x lo_y hi_y lo_z hi_z]
   double v[6];

@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
           if (GC && l > 0) mma(0u, O_WCT + (uint32_t)(l - 1) * 2u * kBB, kBB, idesc32, l < 4 ? 1u : 0u);   // D_gc (+)= ga_l . M_{l-1}
         });
       }
-      if (WS && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);   // under the products
+      // c_dim 32: the weight-gradient kernel rebuilds ga_l from gh_l and the ReLU bits, so only GH is stashed
+      if (WS && CD == 64 && valid) stash_half(a.GA + (int64_t)l * 32 * N, N, n, gh);   // under the products
       if (l > 0 || EMB) {
         wait_mma();
         if (l > 0) tmem_ld16(tm_lane + 32u + col0, gh);

@@ -77,7 +77,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (done) break;
-    if (polls > (1u << 24)) __trap();
+    if (polls > (1u << 20)) __trap();
   }
 }
 
