@@ -214,13 +214,49 @@ def run_ours(args):
         gs = P.graphs.GraphedStep(step_body, generators=[gen], warmup=3)
         graph["g"], graph["loss"], graph["launches"] = gs, gs.out, gs.launches
 
+    # e2e: every step copies one RGB-D frame + the poses from pinned host memory and reads the loss back.  The copy
+    # for step i+1 runs on a second stream while step i computes (what a mapper does with its next keyframe); it
+    # lands in a staging buffer, a device-to-device copy moves it into the graph's static inputs, and the step does
+    # not end before its prefetch has: every byte moves inside a timed region, one frame per step.
+    copy_stream = torch.cuda.Stream()
+    staging = [(torch.empty_like(frames[0][0]), torch.empty_like(frames[0][1]), torch.empty_like(poses_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    pipe = {"i": 0, "primed": False}
+
+    def h2d_async(slot):
+        with torch.cuda.stream(copy_stream):
+            d, c, p = staging[slot]
+            d.copy_(pinned_depth, non_blocking=True)
+            c.copy_(pinned_color, non_blocking=True)
+            p.copy_(pinned_poses, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def step(e2e=False):
         if graph["g"] is None:
             return eager_step(e2e)
-        if e2e:
+        if not e2e:
+            graph["g"]()
+            return None
+        if e2e == "serial":                    # reference point: copy, then compute, on one stream
             h2d_inputs()
+            graph["g"]()
+            return graph["loss"].item()
+        main = torch.cuda.current_stream()
+        slot = pipe["i"] & 1
+        if not pipe["primed"]:                 # very first e2e step: its own copy, not overlapped
+            copy_stream.wait_stream(main)
+            h2d_async(slot)
+            pipe["primed"] = True
+        main.wait_event(ready[slot])
+        d, c, p = staging[slot]
+        frames[0][0].copy_(d); frames[0][1].copy_(c); poses_dev.copy_(p)
+        copy_stream.wait_stream(main)          # staging[slot ^ 1] was consumed by the previous step
+        h2d_async(slot ^ 1)                    # next step's inputs travel while this step computes
         graph["g"]()
-        return graph["loss"].item() if e2e else None
+        out = graph["loss"].item()             # device -> host read of the step's result
+        main.wait_event(ready[slot ^ 1])       # the prefetch belongs to this step's timed region
+        pipe["i"] += 1
+        return out
 
     def timed(k, e2e, profile):
         L.PROFILE = {} if profile else None
@@ -274,11 +310,12 @@ def run_ours(args):
     ms_total, launches, _, _ = timed(args.steps, False, False)
     clocks = sampler.stop() if rank == 0 else None
     if args.light:
-        ms_e2e = ms_total
+        ms_e2e = ms_e2e_serial = ms_total
     else:
         for _ in range(2):
             step(True)
         ms_e2e, _, _, _ = timed(args.steps, True, False)
+        ms_e2e_serial, _, _, _ = timed(args.steps, "serial", False) if use_graph else (ms_e2e, 0, None, 0)
 
     rays_per_step = N_KEYFRAMES * PIX_PER_KF * world
     value = rays_per_step * args.steps / (ms_total * 1e-3)
@@ -336,7 +373,10 @@ def run_ours(args):
                        "eager_ms_per_step": round(ms_eager / args.steps, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s",
                     "h2d_bytes_per_step": pinned_depth.numel() * 4 + pinned_color.numel() * 4 + pinned_poses.numel() * 4,
-                    "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 4)},
+                    "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 4),
+                    "h2d": "next step's frame prefetched on a copy stream while the current step computes; "
+                           "a step ends only after its prefetch has landed",
+                    "serial_ms_per_step": round(ms_e2e_serial / args.steps, 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "roofline_step": {"bytes_per_ray": BYTES_PER_RAY_STEP, "frac_of_hbm_per_gpu": round(step_frac, 4),
                               "peak": hbm, "peak_source": which}}

@@ -258,6 +258,10 @@ int pn_points_to_rays_bwd(const float* g_pts, const double* z, int64_t R, int S,
 /* tcgen05 self-test: Y (128,32) = X (128,K) . W (32,K)^T through the 3xTF32 tensor-core path
  * (operands in shared memory, accumulator in tensor memory); K multiple of 8, <= 128. */
 int pn_tc_selftest(const float* X, const float* W, float* Y, int K, void* stream);
+/* Hardware probe: the same product with MN-major (sample-contiguous) operands Xt (K,128), Wt (K,32); swap selects
+ * which of LBO / SBO is the stride between core matrices along K.  On sm_100a kind::tf32 returns zeros for both
+ * conventions with the no-swizzle layout, which is why the weight-gradient kernels transpose in shared memory. */
+int pn_tc_selftest_mn(const float* Xt, const float* Wt, float* Y, int K, int swap, void* stream);
 
 /* -------- utilities -------- */
 /* (1,32,Z,Y,X) contiguous <-> channels-last [Z][Y][X][32]; `to_channels_last` = 1 or 0. */
