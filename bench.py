@@ -178,10 +178,9 @@ def run_ours(args):
     n_arena = sum(g.numel() for k, g in grids.items() if k != "grid_coarse") + N_KEYFRAMES * PIX_PER_KF * S * 3 + 262144
     arena = E.GradArena(n_arena, dev)
     E.GRAD_ARENA = arena
-    reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "arena" else None)
-    comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "0"))
-    if world > 1 and comm_sms > 0:   # leave SMs free so that NCCL kernels can run beside the persistent decoder kernels
-        L.lib().pn_reserve_sms(comm_sms)
+    comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "0"))   # SMs left to NCCL while gradient all-reduces are in flight
+    reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "arena" else None,
+                                      reserve_sms=comm_sms if world > 1 else 0)
 
     def h2d_inputs():   # host -> device copy of this step's inputs from pinned memory (e2e only)
         frames[0][0].copy_(pinned_depth, non_blocking=True)

@@ -119,11 +119,16 @@ class OverlappedGradReducer:
                    others=[cam.grad for cam in cams])
     """
 
-    def __init__(self, arena=None):
+    def __init__(self, arena=None, reserve_sms: int = 0):
         """With ``arena`` (an engine.GradArena that the backward allocates from) the hook only
-        records the buffers and ``finish`` issues ONE all-reduce over the used part of the arena."""
+        records the buffers and ``finish`` issues ONE all-reduce over the used part of the arena.
+        ``reserve_sms`` > 0: from the first started all-reduce to the end of the backward the
+        persistent decoder kernels leave that many SMs free (``pn_reserve_sms``), so that NCCL's
+        CTAs run beside them instead of in the gaps between them."""
         self.items = []    # (key, tensor or list, flat buffer reduced, work)
         self.arena = arena
+        self.reserve_sms = int(reserve_sms)
+        self._reserved = False
 
     def __enter__(self):
         from . import engine
@@ -134,7 +139,17 @@ class OverlappedGradReducer:
     def __exit__(self, *exc):
         from . import engine
         engine.GRAD_READY_HOOK = self._prev
+        if self._reserved:
+            from . import _lib as L
+            L.lib().pn_reserve_sms(0)
+            self._reserved = False
         return False
+
+    def _reserve(self):
+        if self.reserve_sms > 0 and not self._reserved:
+            from . import _lib as L
+            L.lib().pn_reserve_sms(self.reserve_sms)
+            self._reserved = True
 
     def _ready(self, key, grad):
         if world_size() == 1:
@@ -157,6 +172,7 @@ class OverlappedGradReducer:
         view = grad.permute(0, 2, 3, 4, 1) if (grad.dim() == 5 and not grad.is_contiguous()) else grad
         if view.is_contiguous():
             work = dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True)
+            self._reserve()
             self.items.append((key, grad, view, work))
         else:
             self.items.append((key, grad, None, None))
