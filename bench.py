@@ -79,55 +79,80 @@ def keyframe_poses(rank):
     return c2w[sel]
 
 
+_NVML_POLL = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+while True:
+    print(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx, int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h)), flush=True)
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons DURING the timed region: NVML polled every ~2 ms (the timed region of a default run
-    is a few tens of milliseconds), `nvidia-smi -lms` as the fallback."""
+    """SM clock / throttle reasons DURING the timed region.  A helper PROCESS polls NVML every millisecond (a thread
+    of this process would starve behind the launch loop's GIL; `nvidia-smi -lms` cannot go below 100 ms while a default
+    timed region lasts ~30 ms); `nvidia-smi -lms 100` is the fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
-        self.sm, self.mx, self.reasons, self._stop_evt, self.source = [], [], set(), threading.Event(), None
+        self.index, self.proc = index, None
+        self.sm, self.mx, self.reasons, self.source = [], [], set(), None
+        self.first = threading.Event()
 
-    def _run_nvml(self):
-        import pynvml as N
-        N.nvmlInit()
-        h = N.nvmlDeviceGetHandleByIndex(self.index)
-        self.mx.append(float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)))
-        self.source = "nvml"
-        while not self._stop_evt.is_set():
-            self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
-            mask = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+    def _read_nvml(self):
+        self.proc = subprocess.Popen([sys.executable, "-c", _NVML_POLL, str(self.index)], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            f = line.split()
+            if len(f) != 3:
+                continue
+            self.source = "nvml"
+            self.sm.append(float(f[0])); self.mx.append(float(f[1]))
             for name, bit in self.BITS.items():
-                if mask & bit:
+                if int(f[2]) & bit:
                     self.reasons.add(name)
-            time.sleep(0.002)
+            self.first.set()
 
-    def _run_smi(self):
-        self.source = "nvidia-smi"
+    def _read_smi(self):
         self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         for line in self.proc.stdout:
             r = [x.strip() for x in line.split(",")]
             if len(r) >= 9 and r[1].replace(".", "").isdigit() and r[2].replace(".", "").isdigit():
+                self.source = "nvidia-smi"
                 self.sm.append(float(r[1])); self.mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         self.reasons.add(name)
+                self.first.set()
 
     def run(self):
         try:
-            self._run_nvml()
+            self._read_nvml()
         except Exception:
+            pass
+        if not self.sm and not self._stopping:
             try:
-                self._run_smi()
+                self._read_smi()
             except Exception:
                 pass
 
+    _stopping = False
+
+    def begin(self):
+        """Start polling; returns once the first sample has arrived (or after 3 s); samples taken before are dropped."""
+        self.start()
+        self.first.wait(3.0)
+        del self.sm[:-1]
+
     def stop(self):
-        self._stop_evt.set()
+        self._stopping = True
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
@@ -199,10 +224,13 @@ def run_ours(args):
         ro, rd, gd, gc = torch.cat(ro), torch.cat(rd), torch.cat(gd), torch.cat(gc)
         renderer.depth_max_override = D.share_depth_max(gd) if world > 1 else None
         depth, var, color = renderer.render_batch_ray(grids, model, rd, ro, dev, "color", gt_depth=gd)
-        m = gd > 0
-        # Mapper.py:641-646 (masked L1 depth + weighted L1 colour), written without boolean indexing so that
-        # the host does not synchronise in the middle of the step
-        loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
+        # Mapper.py:641-646 (masked L1 depth + weighted L1 colour): the package's fused loss head (one launch for the
+        # value and its gradient, no host synchronisation); PN_BENCH_TORCH_LOSS=1 keeps the caller-side torch expression
+        if os.environ.get("PN_BENCH_TORCH_LOSS"):
+            m = gd > 0
+            loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
+        else:
+            loss = P.losses.mapping_loss(depth, color, gd, gc, "color", W_COLOR)
         if world > 1 and os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "simple":
             arena.reset()
             loss.backward()
@@ -327,10 +355,7 @@ def run_ours(args):
         step(False)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        t_wait = time.perf_counter()
-        while sampler.source is None and time.perf_counter() - t_wait < 0.5:   # NVML is up before the timed region starts
-            time.sleep(0.005)
+        sampler.begin()
     ms_total, launches, _, _ = timed(args.steps, False, False)
     clocks = sampler.stop() if rank == 0 else None
     if args.light:

@@ -255,6 +255,13 @@ int pn_composite_bwd(const float* raw, const double* z, const float* rays_d, int
 int pn_points_to_rays_bwd(const float* g_pts, const double* z, int64_t R, int S,
                           float* g_rays_o, float* g_rays_d, void* stream);
 
+/* -------- loss head of the mapping iteration (src/Mapper.py:628-646) -------- */
+/* loss = sum_{gt_depth>0} |gt_depth - depth|  (+ w_color * sum |gt_color - color| when use_color), float64 scalar;
+ * also its gradient: g_depth (R) float64, g_color (R,3) float32 (already scaled by w_color).  One CTA with a fixed
+ * summation order (deterministic); the colour sum is rounded to float32 before scaling, as in the reference. */
+int pn_mapping_loss(const double* depth, const float* color, const float* gt_depth, const float* gt_color, int64_t R,
+                    int use_color, float w_color, double* loss, double* g_depth, float* g_color, void* stream);
+
 /* tcgen05 self-test: Y (128,32) = X (128,K) . W (32,K)^T through the 3xTF32 tensor-core path
  * (operands in shared memory, accumulator in tensor memory); K multiple of 8, <= 128. */
 int pn_tc_selftest(const float* X, const float* W, float* Y, int K, void* stream);

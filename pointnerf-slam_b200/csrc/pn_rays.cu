@@ -551,6 +551,46 @@ __global__ void __launch_bounds__(1024) k_max_f32(const float* __restrict__ x, i
   }
 }
 
+// ---------------------------------------------------------------------------
+// Mapper loss head (src/Mapper.py:628-646) with its gradient, one launch.
+// One CTA, fixed summation order (thread-strided partial sums, shuffle + shared tree): deterministic.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_mapping_loss(const double* __restrict__ depth, const float* __restrict__ color,
+                                                       const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
+                                                       int64_t R, int use_color, float w_color, double* __restrict__ loss,
+                                                       double* __restrict__ g_depth, float* __restrict__ g_color) {
+  __shared__ double red_d[32], red_c[32];
+  double sd = 0.0, sc = 0.0;
+  for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {
+    const float g = gt_depth[r];
+    const double diff = (double)g - depth[r];      // float32 - float64 promotes to float64 (torch)
+    const bool m = g > 0.f;
+    if (m) sd += fabs(diff);
+    // d|gt - depth| / d depth = -sign(gt - depth), sign(0) = 0
+    g_depth[r] = m ? (diff > 0.0 ? -1.0 : (diff < 0.0 ? 1.0 : 0.0)) : 0.0;
+    if (use_color) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float dc = __fsub_rn(gt_color[3 * r + a], color[3 * r + a]);
+        sc += (double)fabsf(dc);
+        g_color[3 * r + a] = dc > 0.f ? -w_color : (dc < 0.f ? w_color : 0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sd += __shfl_xor_sync(kFull, sd, o); sc += __shfl_xor_sync(kFull, sc, o); }
+  if ((threadIdx.x & 31) == 0) { red_d[threadIdx.x >> 5] = sd; red_c[threadIdx.x >> 5] = sc; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    sd = threadIdx.x < (blockDim.x >> 5) ? red_d[threadIdx.x] : 0.0;
+    sc = threadIdx.x < (blockDim.x >> 5) ? red_c[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sd += __shfl_xor_sync(kFull, sd, o); sc += __shfl_xor_sync(kFull, sc, o); }
+    // the reference sums the colour residuals in float32 and scales in float32 before adding to the float64 depth term
+    if (threadIdx.x == 0) *loss = use_color ? sd + (double)__fmul_rn(w_color, (float)sc) : sd;
+  }
+}
+
 }  // namespace
 }  // namespace pn
 
@@ -696,6 +736,16 @@ extern "C" int pn_grid_transpose(const float* src, float* dst, int D, int H, int
   const int64_t V = (int64_t)D * H * W;
   k_grid_transpose<<<(unsigned)((V + 31) / 32), 256, 0, PN_ST>>>(src, dst, V, to_channels_last);
   return launch_status("k_grid_transpose");
+}
+
+extern "C" int pn_mapping_loss(const double* depth, const float* color, const float* gt_depth, const float* gt_color, int64_t R,
+                               int use_color, float w_color, double* loss, double* g_depth, float* g_color, void* stream) {
+  if (!depth || !gt_depth || !loss || !g_depth || R < 0 || (use_color && (!color || !gt_color || !g_color))) {
+    set_error("pn_mapping_loss: bad arguments");
+    return 1;
+  }
+  k_mapping_loss<<<1, 1024, 0, PN_ST>>>(depth, color, gt_depth, gt_color, R, use_color, w_color, loss, g_depth, g_color);
+  return launch_status("k_mapping_loss");
 }
 
 extern "C" int pn_max_f32(const float* x, int64_t n, float* out, void* stream) {

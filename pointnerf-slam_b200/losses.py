@@ -1,0 +1,57 @@
+"""Loss head of the mapping iteration (src/Mapper.py:628-646) as one kernel.
+
+The reference computes ``|gt_depth[m] - depth[m]|.sum() + w_color * |gt_color - color|.sum()`` with ~10 elementwise
+and reduction launches (and as many again in the backward); here the value and its gradient come from ONE launch,
+and the backward is two scalings by the upstream gradient.  Optional: the callers' torch expression keeps working.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+class _MappingLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, color, gt_depth, gt_color, w_color, use_color):
+        dev = depth.device
+        d = depth.detach().double().contiguous()
+        gd = gt_depth.detach().float().contiguous()
+        R = d.shape[0]
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        g_depth = torch.empty(R, dtype=torch.float64, device=dev)
+        c = gc = g_color = None
+        if use_color:
+            c = color.detach().float().contiguous()
+            gc = gt_color.detach().float().contiguous()
+            g_color = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        with L.device_guard(dev):
+            L.check(L.lib().pn_mapping_loss(C.c_void_p(d.data_ptr()), C.c_void_p(L.ptr(c)), C.c_void_p(gd.data_ptr()),
+                                            C.c_void_p(L.ptr(gc)), C.c_int64(R), int(use_color), C.c_float(w_color),
+                                            C.c_void_p(loss.data_ptr()), C.c_void_p(g_depth.data_ptr()),
+                                            C.c_void_p(L.ptr(g_color)), C.c_void_p(L.stream_ptr(dev))), "pn_mapping_loss")
+        ctx.save_for_backward(g_depth, g_color)
+        ctx.color_dtype = color.dtype if use_color else None
+        ctx.depth_dtype = depth.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        g_depth, g_color = ctx.saved_tensors
+        gd = (g_depth * go).to(ctx.depth_dtype) if ctx.needs_input_grad[0] else None
+        gc = (g_color * go.float()).to(ctx.color_dtype) if (g_color is not None and ctx.needs_input_grad[1]) else None
+        return gd, gc, None, None, None, None
+
+
+def mapping_loss(depth: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
+                 gt_color: Optional[torch.Tensor], stage: str = "color", w_color: float = 0.2, nice: bool = True) -> torch.Tensor:
+    """Mapper.py:628-646: masked L1 depth loss, plus ``w_color`` times the L1 colour loss in stage
+    ``color`` (always for iMAP*).  Returns a float64 scalar; differentiable w.r.t. depth and colour."""
+    if not depth.is_cuda:
+        raise RuntimeError("pointnerf_slam_b200.losses.mapping_loss needs CUDA tensors (there is no CPU path)")
+    use_color = ((not nice) or stage == "color") and color is not None and gt_color is not None
+    return _MappingLossFn.apply(depth, color if use_color else None, gt_depth, gt_color if use_color else None,
+                                float(w_color), bool(use_color))

@@ -12,7 +12,7 @@ if not _os.path.isdir(_real):
 __path__.insert(0, _real)
 __doc__ = open(_os.path.join(_real, "__init__.py")).read().split('"""')[1]
 
-from . import _lib, engine, common, decoder, config, renderer, graphs  # noqa: E402,F401
+from . import _lib, engine, common, decoder, config, renderer, graphs, losses  # noqa: E402,F401
 from .renderer import Renderer  # noqa: E402,F401
 from .decoder import NICE, MLP, MLP_no_xyz  # noqa: E402,F401
 from .config import get_model, load_bound, grid_init, attach_bounds  # noqa: E402,F401

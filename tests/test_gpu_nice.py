@@ -283,3 +283,32 @@ def test_graphed_step_replays_the_eager_iteration():
     torch.testing.assert_close(cam.grad, ref_grad, rtol=1e-4, atol=1e-7)
     step.release()
     renderer.freeze_map = False
+
+
+@pytest.mark.parametrize("stage", ["color", "fine"])
+def test_mapping_loss_head_matches_oracle(stage):
+    """losses.mapping_loss (Mapper.py:628-646): value and gradients vs the oracle's torch expression."""
+    import pointnerf_slam_b200 as P
+    g = torch.Generator().manual_seed(11)
+    R = 5003
+    depth = (1.0 + torch.rand(R, generator=g, dtype=torch.float64)).requires_grad_(True)
+    color = torch.rand(R, 3, generator=g).requires_grad_(True)
+    gt_depth = 1.0 + torch.rand(R, generator=g)
+    gt_depth[torch.rand(R, generator=g) < 0.1] = 0.0
+    gt_depth[7] = float(depth[7].detach().float())      # an exact tie: sign(0) = 0 in both
+    gt_color = torch.rand(R, 3, generator=g)
+    ref = O.mapping_loss(depth, color, gt_depth, gt_color, stage, 0.2)
+    (3.0 * ref).backward()
+    dd = depth.detach().cuda().requires_grad_(True)
+    cc = color.detach().cuda().requires_grad_(True)
+    out = P.losses.mapping_loss(dd, cc, gt_depth.cuda(), gt_color.cuda(), stage, 0.2)
+    assert out.dtype == torch.float64 and out.dim() == 0
+    (3.0 * out).backward()
+    assert abs(out.item() - ref.item()) <= 2e-6 * abs(ref.item())     # float32 colour sum: summation order differs
+    torch.testing.assert_close(dd.grad.cpu(), depth.grad, rtol=0, atol=0)
+    if stage == "color":
+        torch.testing.assert_close(cc.grad.cpu(), color.grad, rtol=0, atol=0)
+    else:
+        assert cc.grad is None
+    again = P.losses.mapping_loss(dd, cc, gt_depth.cuda(), gt_color.cuda(), stage, 0.2)
+    assert again.item() == out.item(), "fixed summation order: run-to-run deterministic"
