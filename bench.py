@@ -379,10 +379,9 @@ def run_ours(args):
     # per sample per grid read, plus 2048 B per sample read-modify-write of the gradient grid in backward
     alg = {"grid_mlp_fwd:color": 1, "grid_mlp_fwd:fine": 2, "grid_mlp_fwd:middle": 1,
            "grid_mlp_bwd:color": 3, "grid_mlp_bwd:fine": 3, "grid_mlp_bwd:middle": 3}
-    # the weight-gradient call (k_wgrad_tc + k_wgrad_out + k_wgrad_B) must read its operands once:
-    # h0..h3, emb, c, GA, GH for the tensor-core GEMM (128 + 96 + 32 + 160 + 160 floats per sample), h4 and the
-    # output gradient for the output layer (32 + 4), the embedding-argument gradient and the point for B (96 + 3)
-    alg_wgrad = n_samples * (128 + 96 + 32 + 160 + 160 + 32 + 4 + 96 + 3) * 4
+    # the weight-gradient kernel (k_wgrad_tc32) must read its operands once: h0..h4, emb, c, GH, the embedding-argument
+    # gradient, the output gradient and the point (160 + 96 + 32 + 160 + 96 + 4 + 3 floats per sample) + 20 B of ReLU masks
+    alg_wgrad = n_samples * ((160 + 96 + 32 + 160 + 96 + 4 + 3) * 4 + 20)
     # measured DRAM traffic per launch of the same kernels (ncu --set full, profiles/r1_dram_traffic_per_launch.json)
     ncu_name = {"grid_mlp_fwd:color": "k_grid_mlp_fwd_tc<32, 4>", "grid_mlp_fwd:fine": "k_grid_mlp_fwd_tc<64, 1>",
                 "grid_mlp_fwd:middle": "k_grid_mlp_fwd_tc<32, 1>", "grid_mlp_bwd:color": "k_grid_mlp_bwd_tc<32, 4, 1, 1, 1>",
@@ -393,8 +392,10 @@ def run_ours(args):
     if top in ncu_name and os.path.exists(tpath):
         per_launch = json.load(open(tpath))
         traffic = per_launch.get(ncu_name[top])
-        if top.startswith("grid_mlp_wgrad") and traffic is not None:   # the call is three kernels
-            traffic += per_launch.get("k_wgrad_out", 0) + per_launch.get("k_wgrad_B", 0)
+        if top.startswith("grid_mlp_wgrad"):   # c_dim 32: one fused kernel; otherwise the call is three kernels
+            traffic = per_launch.get("k_wgrad_tc32")
+            if traffic is None and "k_wgrad_tc" in per_launch:
+                traffic = per_launch["k_wgrad_tc"] + per_launch.get("k_wgrad_out", 0) + per_launch.get("k_wgrad_B", 0)
     roofline = None
     if top is not None:
         dur_ms = statistics.mean(kern[top])

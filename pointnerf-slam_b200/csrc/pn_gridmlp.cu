@@ -864,9 +864,14 @@ extern "C" int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash
   }
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tensor_cores() && w->c_dim == 32 && stash->relu_bits)   // one fused tensor-core kernel (GA = GH masked by the ReLU bits)
+  if (use_tensor_cores() && w->c_dim == 32) {   // one fused tensor-core kernel (GA = GH masked by the ReLU bits)
+    if (!stash->relu_bits) {   // the tensor-core backward does not write GA for c_dim 32
+      set_error("pn_grid_mlp_wgrad: stash->relu_bits is required");
+      return 1;
+    }
     return launch_wgrad_tc32(N, w->n_out, stash->H, stash->C, stash->E, ws->GH, ws->GARG, ws->GO, ws->P32, stash->relu_bits, g->W,
                              g->b, g->Wc, g->bc, g->Wo, g->bo, g->B, st);
+  }
   const int64_t blk = 32 * N;  // floats per planar-4 (N x 32) block
   WgArgs a;
   a.N = N;

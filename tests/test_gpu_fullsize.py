@@ -197,3 +197,21 @@ def test_render_img_full_frame(world):
         dr, vr, cr = O.render_batch_ray(sc, rd[sel], ro[sel], "color", gd[sel])
     torch.testing.assert_close(d.reshape(-1)[sel].cpu(), dr, **OUT_TOL)
     torch.testing.assert_close(c.reshape(-1, 3)[sel].cpu(), cr, **OUT_TOL)
+
+
+def test_sample_depths_when_the_ray_leaves_the_box_at_once(world):
+    """far < near (the ray exits the scene box right after its origin): the uniform run is DEscending, so the
+    z-value kernel must take its general sort instead of the merge of two ascending runs (Renderer.py:98-157)."""
+    w = world
+    hi = w.bound[:, 1].float()
+    n = 64
+    ro = (hi - 1e-3).repeat(n, 1).to(DEV)
+    rd = torch.nn.functional.normalize(torch.tensor([[1.0, 1.0, 1.0]]).repeat(n, 1) + 0.1 * torch.rand(n, 3), dim=-1).to(DEV)
+    gd = (1.5 + torch.rand(n)).to(DEV)
+    gd[::7] = 0.0                                   # and the zero-depth branch next to it
+    z = w.renderer.sample_z(rd, ro, gd)
+    zr = O.ray_z_values(_oracle_scene(w), ro.cpu(), rd.cpu(), gd.cpu())
+    assert torch.equal(z.cpu(), zr)
+    assert bool((z[:, 1:] >= z[:, :-1]).all())
+    uniform_far = zr[0].max()
+    assert float(uniform_far) > 0.0
