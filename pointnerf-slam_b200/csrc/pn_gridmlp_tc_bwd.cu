@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
   };
 
   const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
-  for (int64_t t = (int64_t)blockIdx.x * kGroups + grp; t < ntiles; t += (int64_t)gridDim.x * kGroups) {
+  // tile order as in the forward: the partial last wave is spread over the SMs instead of filling whole CTAs
+  for (int64_t t = (int64_t)blockIdx.x + (int64_t)gridDim.x * grp; t < ntiles; t += (int64_t)gridDim.x * kGroups) {
     const int64_t n = t * 128 + row;
     const bool valid = n < N;
     Sample sp;
@@ -329,8 +330,8 @@ template <int CD, int NOUT, bool GG, bool DP, bool WS>
 int launch_t(const BwdArgs& a, cudaStream_t st) {
   auto kern = k_grid_mlp_bwd_tc<CD, NOUT, GG, DP, WS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmem);
-  const int64_t per_cta = ((a.pts.N + 127) / 128 + tcb::kGroups - 1) / tcb::kGroups;
-  const int grid = (int)((per_cta < (int64_t)sm_count()) ? per_cta : (int64_t)sm_count());
+  const int64_t ntiles = (a.pts.N + 127) / 128;   // fewer tiles than SMs: one tile (group 0) per CTA
+  const int grid = (int)((ntiles < (int64_t)sm_count()) ? ntiles : (int64_t)sm_count());
   kern<<<grid, tcb::kGroups * 256, tcb::kSmem, st>>>(a);
   return launch_status("k_grid_mlp_bwd_tc");
 }

@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   };
 
   const int64_t N = a.pts.N, ntiles = (N + 127) / 128;
-  for (int64_t t = (int64_t)blockIdx.x * 2 + grp; t < ntiles; t += (int64_t)gridDim.x * 2) {
+  // Tile order: a wave fills group 0 of every CTA before group 1, so the partial last wave is spread over as many
+  // SMs as possible (a group that runs alone on its SM finishes its tile much sooner than one that shares it).
+  for (int64_t t = (int64_t)blockIdx.x + (int64_t)gridDim.x * grp; t < ntiles; t += (int64_t)gridDim.x * 2) {
     const int64_t n = t * 128 + row;
     const bool valid = n < N;
     Sample sp;
@@ -265,8 +267,8 @@ int launch_t(const FwdArgs& a, cudaStream_t st) {
   auto kern = k_grid_mlp_fwd_tc<CD, NOUT>;
   const size_t sm = tc::smem_total<CD>();
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  const int64_t pairs = ((a.pts.N + 127) / 128 + 1) / 2;
-  const int grid = (int)((pairs < (int64_t)sm_count()) ? pairs : (int64_t)sm_count());
+  const int64_t ntiles = (a.pts.N + 127) / 128;   // fewer tiles than SMs: one tile (group 0) per CTA
+  const int grid = (int)((ntiles < (int64_t)sm_count()) ? ntiles : (int64_t)sm_count());
   kern<<<grid, 512, sm, st>>>(a);
   return launch_status("k_grid_mlp_fwd_tc");
 }
