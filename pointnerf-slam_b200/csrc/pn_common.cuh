@@ -32,6 +32,28 @@ int launch_wgrad_tc32(int64_t N, int n_out, const float* H, const float* C, cons
                       const float* GO, const float* P32, const uint32_t* relu_bits, float* const* W, float* const* b,
                       float* const* Wc, float* const* bc, float* Wo, float* bo, float* B, cudaStream_t st);
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// The persistent decoder kernels start with a prologue that does not depend on the previous kernel
+// of the stream (weights -> shared memory, TMEM allocation).  Launched with the programmatic-
+// serialization attribute, a kernel is scheduled as soon as every CTA of its predecessor has called
+// pdl_launch_dependents() (they do so at once) and an SM frees up, runs its prologue while the
+// predecessor drains, and calls pdl_wait() -- which returns when the predecessor has completed and
+// its writes are visible -- before touching anything the predecessor may have produced.  After a
+// kernel that never triggers (any other kernel) the attribute changes nothing.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 struct Bound6 {  // [lo_x hi_x lo_y hi_y lo_z hi_z]
   double v[6];
 };

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
   unsigned char* a_hi = smraw + O_A + (uint32_t)grp * 2u * kABytes;
   unsigned char* a_lo = a_hi + kABytes;
   float* gtile = reinterpret_cast<float*>(a_hi);   // [128][36] floats, valid between the last MMA and the next tile
+  pdl_launch_dependents();   // prologue below is independent of the previous kernel
   if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) { for (int i = 0; i < kGroups; ++i) umma::mbar_init(&bars[i], 1); umma::fence_mbar_init(); }
   stage_bt(smraw + O_WT, kBB, a.w.W[1], 32, 0, 32, 32);
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(tcb::kGroups * 256, 1) k_grid_mlp_bwd_tc(const
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  pdl_wait();   // gradients, stash and masks written by earlier kernels are read from here on
   const uint32_t tm = tmem_base_s + (uint32_t)grp * 160u;
   const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);
   const uint32_t sA = umma::smem_u32(a_hi), sW = umma::smem_u32(smraw);
@@ -332,7 +334,7 @@ int launch_t(const BwdArgs& a, cudaStream_t st) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmem);
   const int64_t ntiles = (a.pts.N + 127) / 128;   // fewer tiles than SMs: one tile (group 0) per CTA
   const int grid = (int)((ntiles < (int64_t)sm_count()) ? ntiles : (int64_t)sm_count());
-  kern<<<grid, tcb::kGroups * 256, tcb::kSmem, st>>>(a);
+  launch_pdl(kern, dim3(grid), dim3(tcb::kGroups * 256), (size_t)tcb::kSmem, st, a);
   return launch_status("k_grid_mlp_bwd_tc");
 }
 

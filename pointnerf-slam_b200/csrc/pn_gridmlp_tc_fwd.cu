@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sm + S_TOTAL + 4);
   unsigned char* a_hi = smraw + o_a<CD>() + (uint32_t)grp * 2u * kABytes;
   unsigned char* a_lo = a_hi + kABytes;
-  // ---- one-time set-up: TMEM, barriers, weights
+  // ---- one-time set-up: TMEM, barriers, weights (independent of the previous kernel: see pdl_wait below)
+  pdl_launch_dependents();
   if (tid < 32) umma::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::fence_mbar_init(); }
   constexpr uint32_t O_WC = o_wc<CD>();
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  pdl_wait();   // everything below may read what the previous kernel of the stream wrote (raw, stash, grids)
   const uint32_t tm = tmem_base_s + (uint32_t)grp * 256u;               // this group's columns
   const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);        // this warp's lanes
   const uint32_t sA = umma::smem_u32(a_hi), sAlo = sA + kABytes;
@@ -269,7 +271,7 @@ int launch_t(const FwdArgs& a, cudaStream_t st) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   const int64_t ntiles = (a.pts.N + 127) / 128;   // fewer tiles than SMs: one tile (group 0) per CTA
   const int grid = (int)((ntiles < (int64_t)sm_count()) ? ntiles : (int64_t)sm_count());
-  kern<<<grid, 512, sm, st>>>(a);
+  launch_pdl(kern, dim3(grid), dim3(512), sm, st, a);
   return launch_status("k_grid_mlp_fwd_tc");
 }
 

@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(kWg32Threads, 1) k_wgrad_tc32(const WgTc32Args
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smraw + P_END + 48);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t N = a.N;
+  pdl_launch_dependents();
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&full[i], 256); umma::mbar_init(&empty[i], 1); }
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(kWg32Threads, 1) k_wgrad_tc32(const WgTc32Args
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  pdl_wait();   // the stash written by the backward kernel is read from here on
   const uint32_t tm = tmem_base_s;
   const int64_t nchunks = (N + kChunk - 1) / kChunk;
   const int64_t mine = (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x;   // chunks of this CTA: blockIdx.x + k*gridDim.x
@@ -513,7 +515,7 @@ int launch_wgrad_tc32(int64_t N, int n_out, const float* H, const float* C, cons
   cudaFuncSetAttribute(k_wgrad_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem32);
   const int64_t nchunks = (N + kChunk - 1) / kChunk;
   const int grid = (int)(nchunks < (int64_t)sm_count() ? nchunks : (int64_t)sm_count());
-  k_wgrad_tc32<<<grid, kWg32Threads, kSmem32, st>>>(a);
+  launch_pdl(k_wgrad_tc32, dim3(grid), dim3(kWg32Threads), (size_t)kSmem32, st, a);
   return launch_status("k_wgrad_tc32");
 }
 
