@@ -36,16 +36,21 @@ def _as_c2w(c2w, device) -> torch.Tensor:
 
 
 class _CameraFn(torch.autograd.Function):
+    """(7,) -> (3,4) or (B,7) -> (B,3,4).  The single-pose form is handled here (not by unsqueeze / select around
+    the Function) so that its backward is one kernel, without select_backward's zero fill and copy."""
+
     @staticmethod
     def forward(ctx, cam):
-        camc = cam.detach().float().contiguous()
+        single = cam.dim() == 1
+        camc = cam.detach().float().contiguous().reshape(-1, 7)
         B = camc.shape[0]
         out = torch.empty((B, 3, 4), dtype=torch.float32, device=cam.device)
         with L.device_guard(cam.device):
             L.check(L.lib().pn_camera_from_tensor_fwd(C.c_void_p(camc.data_ptr()), B, C.c_void_p(out.data_ptr()),
                                                       C.c_void_p(L.stream_ptr(cam.device))), "pn_camera_from_tensor_fwd")
         ctx.save_for_backward(camc)
-        return out
+        ctx.single, ctx.in_dtype = single, cam.dtype
+        return out[0] if single else out
 
     @staticmethod
     def backward(ctx, g):
@@ -56,15 +61,14 @@ class _CameraFn(torch.autograd.Function):
             L.check(L.lib().pn_camera_from_tensor_bwd(C.c_void_p(camc.data_ptr()), C.c_void_p(g.data_ptr()), camc.shape[0],
                                                       C.c_void_p(out.data_ptr()), C.c_void_p(L.stream_ptr(camc.device))),
                     "pn_camera_from_tensor_bwd")
-        return out
+        out = out[0] if ctx.single else out
+        return out if ctx.in_dtype == torch.float32 else out.to(ctx.in_dtype)
 
 
 def get_camera_from_tensor(inputs: torch.Tensor) -> torch.Tensor:
     """[qw,qx,qy,qz,tx,ty,tz] (7,) or (B,7) -> (3,4) or (B,3,4); differentiable
     (src/common.py:163-176)."""
-    single = inputs.dim() == 1
-    rt = _CameraFn.apply(inputs.unsqueeze(0) if single else inputs)
-    return rt[0] if single else rt
+    return _CameraFn.apply(inputs)
 
 
 def quad2rotation(quad: torch.Tensor) -> torch.Tensor:
