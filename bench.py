@@ -201,11 +201,11 @@ def run_ours(args):
     # small fills (and, on several GPUs, the option of ONE all-reduce over it)
     from pointnerf_slam_b200 import engine as E
     n_arena = sum(g.numel() for k, g in grids.items() if k != "grid_coarse") + N_KEYFRAMES * PIX_PER_KF * S * 3 + 262144
-    arena = E.GradArena(n_arena, dev)
+    ar_mode = os.environ.get("PN_BENCH_ALLREDUCE", "overlap")   # overlap | arena | nvls | simple
+    arena = D.SymmetricGradArena(n_arena, dev) if (world > 1 and ar_mode == "nvls") else E.GradArena(n_arena, dev)
     E.GRAD_ARENA = arena
     comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "0"))   # SMs left to NCCL while gradient all-reduces are in flight
-    reducer = D.OverlappedGradReducer(arena if os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "arena" else None,
-                                      reserve_sms=comm_sms if world > 1 else 0)
+    reducer = D.OverlappedGradReducer(arena if ar_mode in ("arena", "nvls") else None, reserve_sms=comm_sms if world > 1 else 0)
 
     def h2d_inputs():   # host -> device copy of this step's inputs from pinned memory (e2e only)
         frames[0][0].copy_(pinned_depth, non_blocking=True)
@@ -231,7 +231,7 @@ def run_ours(args):
             loss = torch.where(m, torch.abs(gd - depth), torch.zeros_like(depth)).sum() + W_COLOR * torch.abs(gc - color).sum()
         else:
             loss = P.losses.mapping_loss(depth, color, gd, gc, "color", W_COLOR)
-        if world > 1 and os.environ.get("PN_BENCH_ALLREDUCE", "overlap") == "simple":
+        if world > 1 and ar_mode == "simple":
             arena.reset()
             loss.backward()
             D.allreduce_gradients([t.grad for t in trained])

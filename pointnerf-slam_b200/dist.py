@@ -99,6 +99,34 @@ def allreduce_gradients(tensors: Iterable[Optional[torch.Tensor]], small_bytes: 
         dst.copy_(tmp)
 
 
+class SymmetricGradArena:
+    """An ``engine.GradArena`` whose buffer lives in symmetric memory (every rank maps every peer's copy and the
+    NVSwitch multicast address).  ``all_reduce_used`` sums the used part across ranks with the switch's in-fabric
+    reduction: each rank owns 1/N of the range, pulls it with ``multimem.ld_reduce`` (the NVSwitch adds the N
+    replicas) and pushes the sum back with ``multimem.st`` (broadcast) -- PyTorch's ``symm_mem.multimem_all_reduce_``
+    kernel over NVLink peer memory, no NCCL ring.  Needs an NVSwitch box with multicast support."""
+
+    def __new__(cls, numel: int, device, group=None):
+        from .engine import GradArena
+        import torch.distributed._symmetric_memory as symm
+
+        class _Arena(GradArena):
+            def __init__(self, numel, device, group):
+                group = group or dist.group.WORLD
+                self.group_name = group.group_name
+                n = (int(numel) + 4095) // 4096 * 4096
+                self.buf = symm.empty(n, dtype=torch.float32, device=device)
+                self.handle = symm.rendezvous(self.buf, self.group_name)
+                self.buf.zero_()
+                self.offset = 0
+
+            def all_reduce_used(self):
+                n = min((self.offset + 4095) // 4096 * 4096, self.buf.numel())
+                torch.ops.symm_mem.multimem_all_reduce_(self.buf[:n], "sum", self.group_name)
+
+        return _Arena(numel, device, group)
+
+
 def mapping_gradients(params: Sequence[torch.Tensor]) -> List[Optional[torch.Tensor]]:
     return [p.grad for p in params]
 
@@ -183,7 +211,10 @@ class OverlappedGradReducer:
         gradient tensors (poses ...) reduced here in one bucket."""
         late = []
         if self.arena is not None and world_size() > 1 and self.arena.offset:
-            dist.all_reduce(self.arena.used(), op=dist.ReduceOp.SUM)
+            if hasattr(self.arena, "all_reduce_used"):        # symmetric-memory arena: NVLS multimem all-reduce
+                self.arena.all_reduce_used()
+            else:
+                dist.all_reduce(self.arena.used(), op=dist.ReduceOp.SUM)
         for key, grad, buf, work in self.items:
             if work is not None:
                 work.wait()
