@@ -127,6 +127,7 @@ class _SampleRaysFn(torch.autograd.Function):
                                                C.c_void_p(L.ptr(c_out)), C.c_void_p(L.stream_ptr(dev))), "pn_sample_rays_fwd")
         ctx.geom, ctx.idx, ctx.shape = geom, idx, tuple(c2w.shape)
         ctx.mark_non_differentiable(*[t for t in (d_out, c_out) if t is not None])
+        ctx.set_materialize_grads(False)   # no zero tensors for the (non-differentiable) depth / colour outputs
         return ro, rd, d_out, c_out
 
     @staticmethod
@@ -180,6 +181,7 @@ class _ImageRaysFn(torch.autograd.Function):
                                               c2wc.shape[-1], C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()),
                                               C.c_void_p(L.stream_ptr(dev))), "pn_image_rays_fwd")
         ctx.geom, ctx.shape = geom, tuple(c2w.shape)
+        ctx.set_materialize_grads(False)
         return ro, rd
 
     @staticmethod
