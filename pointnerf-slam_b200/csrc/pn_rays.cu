@@ -239,6 +239,85 @@ __global__ void __launch_bounds__(128) k_ray_zvals(const float* __restrict__ ro,
   for (int k = 0; k < S; ++k) zout[r * S + k] = z[k];
 }
 
+// Warp-per-ray form of k_ray_zvals for the common case (no perturbation): lanes compute the samples of both runs,
+// and -- when both runs ascend -- every sample finds its place in the merged row by counting the samples of the
+// other run that precede it (ties: the uniform run first, as in the sequential merge).  Same arithmetic, same
+// values; a descending run is sorted by lane 0.  8 rays per CTA.
+__global__ void __launch_bounds__(256) k_ray_zvals_warp(const float* __restrict__ ro, const float* __restrict__ rd,
+                                                       const float* __restrict__ gt, const float* __restrict__ dmax_p, int64_t R,
+                                                       Bound6 b, int ns, int nsurf, int lindisp, const float* __restrict__ tv,
+                                                       const double* __restrict__ ts, double* __restrict__ zout) {
+  __shared__ double zs[8][PN_MAX_SAMPLES];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 8 + w;
+  if (r >= R) return;
+  double* z = zs[w];
+  double far_bb = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double o = (double)ro[3 * r + a], d = (double)rd[3 * r + a];
+    const double t0 = __ddiv_rn(__dsub_rn(b.v[2 * a], o), d), t1 = __ddiv_rn(__dsub_rn(b.v[2 * a + 1], o), d);
+    const double tm = fmax(t0, t1);
+    far_bb = (a == 0) ? tm : fmin(far_bb, tm);
+  }
+  far_bb = __dadd_rn(far_bb, 0.01);
+  const bool has_gt = gt != nullptr;
+  float g = 0.f, dmax = 0.f;
+  double far = far_bb;
+  if (has_gt) {
+    g = gt[r];
+    dmax = *dmax_p;
+    far = fmin(fmax(far_bb, 0.0), (double)__fmul_rn(dmax, 1.2f));
+  }
+  const float near32 = has_gt ? __fmul_rn(g, 0.01f) : 0.01f;
+  for (int k = lane; k < ns; k += 32) {
+    const float t = tv[k];
+    const float omt = __fsub_rn(1.0f, t);
+    if (!lindisp) {
+      z[k] = __dadd_rn((double)__fmul_rn(near32, omt), __dmul_rn(far, (double)t));
+    } else {
+      const float inv_near = has_gt ? __fdiv_rn(1.0f, near32) : 100.0f;
+      const double a = (double)__fmul_rn(inv_near, omt);
+      const double c = __dmul_rn(__ddiv_rn(1.0, far), (double)t);
+      z[k] = __ddiv_rn(1.0, __dadd_rn(a, c));
+    }
+  }
+  const int S = ns + nsurf;
+  if (nsurf > 0) {
+    const double lo = g > 0.f ? (double)__fmul_rn(0.95f, g) : 0.001, hi = g > 0.f ? (double)__fmul_rn(1.05f, g) : (double)dmax;
+    for (int k = lane; k < nsurf; k += 32) z[ns + k] = __dadd_rn(__dmul_rn(lo, __dsub_rn(1.0, ts[k])), __dmul_rn(hi, ts[k]));
+  }
+  __syncwarp();
+  double* out = zout + r * S;
+  if (nsurf == 0) {
+    for (int k = lane; k < S; k += 32) out[k] = z[k];
+    return;
+  }
+  bool asc = true;
+  for (int k = lane; k < S; k += 32)
+    if (k > 0 && k != ns) asc = asc && (z[k - 1] <= z[k]);
+  if (__all_sync(kFull, asc)) {
+    for (int k = lane; k < S; k += 32) {
+      const double v = z[k];
+      int pos;
+      if (k < ns) {           // uniform sample: surface samples strictly below come first
+        int c = 0;
+        for (int j = ns; j < S; ++j) c += z[j] < v;
+        pos = k + c;
+      } else {                // surface sample: uniform samples below or equal come first
+        int c = 0;
+        for (int j = 0; j < ns; ++j) c += z[j] <= v;
+        pos = (k - ns) + c;
+      }
+      out[pos] = v;
+    }
+  } else {
+    if (lane == 0) insertion_sort(z, S);
+    __syncwarp();
+    for (int k = lane; k < S; k += 32) out[k] = z[k];
+  }
+}
+
 __global__ void __launch_bounds__(128) k_importance(const double* __restrict__ zin, const float* __restrict__ w, int64_t R, int S,
                                                    int ni, const float* __restrict__ u_lin, const float* __restrict__ u_rand,
                                                    double* __restrict__ zout) {
@@ -659,6 +738,11 @@ extern "C" int pn_ray_zvals(const float* rays_o, const float* rays_d, const floa
   }
   if (gt_depth && (!depth_max || (n_surface > 0 && !t_surface))) { set_error("pn_ray_zvals: depth given without depth_max/t_surface"); return 1; }
   if (R == 0) return 0;
+  if (!t_rand) {   // common case: warp per ray
+    k_ray_zvals_warp<<<(unsigned)((R + 7) / 8), 256, 0, PN_ST>>>(rays_o, rays_d, gt_depth, depth_max, R, make_bound(bound), n_samples,
+                                                               gt_depth ? n_surface : 0, lindisp, t_vals, t_surface, z_out);
+    return launch_status("k_ray_zvals_warp");
+  }
   k_ray_zvals<<<(unsigned)((R + 127) / 128), 128, 0, PN_ST>>>(rays_o, rays_d, gt_depth, depth_max, R, make_bound(bound),
                                                              n_samples, gt_depth ? n_surface : 0, lindisp, t_vals,
                                                              t_surface, t_rand, z_out);
