@@ -204,8 +204,9 @@ def run_ours(args):
     ar_mode = os.environ.get("PN_BENCH_ALLREDUCE", "overlap")   # overlap | arena | nvls | simple
     arena = D.SymmetricGradArena(n_arena, dev) if (world > 1 and ar_mode == "nvls") else E.GradArena(n_arena, dev)
     E.GRAD_ARENA = arena
-    # SMs left to NCCL while gradient all-reduces are in flight (measured at N=8: 1.72 -> 1.69 ms with 12-20; no gain at N=2)
-    comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "16" if world >= 4 else "0"))
+    # SMs left to NCCL while gradient all-reduces are in flight (measured: N=8 1.72 -> 1.69 ms with 12-20; N=4 1.58 -> 1.60 ms
+    # with 16; N=2 no gain) -> only from 8 GPUs up by default
+    comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "16" if world >= 8 else "0"))
     reducer = D.OverlappedGradReducer(arena if ar_mode in ("arena", "nvls") else None, reserve_sms=comm_sms if world > 1 else 0)
 
     def h2d_inputs():   # host -> device copy of this step's inputs from pinned memory (e2e only)

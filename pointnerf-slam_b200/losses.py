@@ -41,8 +41,9 @@ class _MappingLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         g_depth, g_color = ctx.saved_tensors
+        # a 0-dim multiplier does not promote the dtype of a dimensioned tensor: one launch each
         gd = (g_depth * go).to(ctx.depth_dtype) if ctx.needs_input_grad[0] else None
-        gc = (g_color * go.float()).to(ctx.color_dtype) if (g_color is not None and ctx.needs_input_grad[1]) else None
+        gc = (g_color * go).to(ctx.color_dtype) if (g_color is not None and ctx.needs_input_grad[1]) else None
         return gd, gc, None, None, None, None
 
 
