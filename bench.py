@@ -374,7 +374,9 @@ def run_ours(args):
     hbm, which = peaks()
     # dominant kernel: largest total event time among the profiled C-ABI calls
     kern = {k: [a.elapsed_time(b) for a, b in v] for k, v in (prof or {}).items()}
-    share = {k: sum(v) / ms_eager for k, v in kern.items()}
+    # share of the TIMED step: kernel durations come from the eager pass (events around each C-ABI call), the
+    # denominator is the timed (graph-replayed, i.e. GPU-bound) step -- the eager step itself is host-bound
+    share = {k: sum(v) / (ms_total if use_graph else ms_eager) for k, v in kern.items()}
     top = max(kern, key=lambda k: sum(kern[k])) if kern else None
     n_samples = N_KEYFRAMES * PIX_PER_KF * S
     # algorithmic bytes per launch of each decoder kernel (DESIGN.md "roofline"): gathers of 1024 B
@@ -407,6 +409,7 @@ def run_ours(args):
                     "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": which,
                     "avg_launch_ms": round(dur_ms, 4), "alg_bytes_per_launch": bytes_launch,
                     "kernel_share_of_step": {k: round(v, 3) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
+                    "kernel_ms": {k: round(statistics.mean(v), 4) for k, v in sorted(kern.items(), key=lambda kv: -sum(kv[1]))},
                     "note": "decoder layers run on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulate in TMEM); the decoder "
                             "kernels are latency/issue-bound (tensor pipe 10-16% active, 16-24 warps/SM), not HBM-bound; the "
                             "weight-gradient call streams the activation stash once (HBM-bound by design); HBM roofline is "
