@@ -11,7 +11,11 @@
 // (The MN-major operand mode, which would take the stash rows unchanged, returns zeros for
 // kind::tf32 on sm_100a -- measured with pn_tc_selftest_mn -- so it is not used.)
 //
-// Per 16-sample chunk (K = 16 = 2 MMA k-steps), M = 128 features, 3xTF32, one wide-N product per A operand:
+// Two kernels share this scheme: k_wgrad_tc32 (further down; c_dim 32, every parameter gradient, warp-specialised
+// producers / issuer) is the one the mapping iteration uses; k_wgrad_tc (below; any c_dim, W / b / Wc / bc only,
+// lock-step stages, followed by k_wgrad_out and k_wgrad_B of pn_gridmlp.cu) remains for c_dim 64.
+//
+// k_wgrad_tc, per 16-sample chunk (K = 16 = 2 MMA k-steps), M = 128 features, 3xTF32, one wide-N product per A operand:
 //     A_H = [h0|h1|h2|h3]   x [GA_3|GA_1|GA_2|GA_4] (N = 128) -> dW3[:, 93:], dW1, dW2, dW4 (diagonal 32-row blocks)
 //     A_E = [emb(96)|0(32)] x [GA_0|GA_3]           (N = 64)  -> dW0, dW3[:, :93]
 //     A_C = [c(CD)|0]       x [GH_0..GH_4]          (N = 160) -> dWc_0..4
