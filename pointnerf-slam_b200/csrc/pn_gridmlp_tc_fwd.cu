@@ -8,7 +8,8 @@ namespace {
 // CTA = 512 threads = two groups of 256.  Inside a group TWO threads serve each of the 128
 // sample rows: warp (quarter q = warp&3, half = warp>>2) owns rows 32q..32q+31 (the TMEM lanes
 // a warp with that id may address) and columns [16*half, 16*half+16) of every 32-wide operand.
-template <int CD, int NOUT>
+// BITS: record the ReLU masks (needed by any backward); inference launches compile the bookkeeping away.
+template <int CD, int NOUT, bool BITS>
 __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using namespace tc;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float pre = d1[j] + sm[S_BIAS + l * 32 + col0 + j];
-        bits |= (pre > 0.f) ? (1u << j) : 0u;
+        if (BITS) bits |= (pre > 0.f) ? (1u << j) : 0u;
         h[j] = fmaxf(pre, 0.f) + s2[j];
       }
       store_half_row(h);
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
       });
       // stash + the next block's feature term, under the product
       if (valid) {
-        if (a.relu_bits) reinterpret_cast<uint16_t*>(a.relu_bits)[((int64_t)l * N + n) * 2 + half] = (uint16_t)bits;
+        if (BITS) reinterpret_cast<uint16_t*>(a.relu_bits)[((int64_t)l * N + n) * 2 + half] = (uint16_t)bits;
         if (a.H) {
           float4* o = reinterpret_cast<float4*>(a.H + (int64_t)l * 32 * N);
 #pragma unroll
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float pre = d1[j] + sm[S_BIAS + 128 + j];
-        bits |= (pre > 0.f) ? (1u << j) : 0u;
+        if (BITS) bits |= (pre > 0.f) ? (1u << j) : 0u;
         h[j] = fmaxf(pre, 0.f) + (d2[j] + sm[S_BC + 128 + j]);
       }
       float out[4] = {0.f, 0.f, 0.f, 0.f};
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
         out[o] = s;
       }
       if (valid) {
-        if (a.relu_bits) a.relu_bits[(int64_t)4 * N + n] = bits;
+        if (BITS) a.relu_bits[(int64_t)4 * N + n] = bits;
         if (a.H) store_planar32(a.H + (int64_t)4 * 32 * N, N, n, h);
         float4* r = reinterpret_cast<float4*>(a.raw) + n;
         const bool force = a.apply_mask && !sp.inside;
@@ -264,15 +265,20 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
 }
 
 
-template <int CD, int NOUT>
-int launch_t(const FwdArgs& a, cudaStream_t st) {
-  auto kern = k_grid_mlp_fwd_tc<CD, NOUT>;
+template <int CD, int NOUT, bool BITS>
+int launch_b(const FwdArgs& a, cudaStream_t st) {
+  auto kern = k_grid_mlp_fwd_tc<CD, NOUT, BITS>;
   const size_t sm = tc::smem_total<CD>();
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   const int64_t ntiles = (a.pts.N + 127) / 128;   // fewer tiles than SMs: one tile (group 0) per CTA
   const int grid = (int)((ntiles < (int64_t)sm_count()) ? ntiles : (int64_t)sm_count());
   launch_pdl(kern, dim3(grid), dim3(512), sm, st, a);
   return launch_status("k_grid_mlp_fwd_tc");
+}
+
+template <int CD, int NOUT>
+int launch_t(const FwdArgs& a, cudaStream_t st) {
+  return a.relu_bits ? launch_b<CD, NOUT, true>(a, st) : launch_b<CD, NOUT, false>(a, st);
 }
 
 }  // namespace
