@@ -311,6 +311,7 @@ def run_ours(args):
 
     def timed(k, e2e, profile):
         L.PROFILE = {} if profile else None
+        E.PARALLEL_BACKWARD = not profile   # per-kernel event times are taken with the backward passes one after another
         evs = []
         if world > 1:
             dist.barrier()
@@ -334,6 +335,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         prof = L.PROFILE
         L.PROFILE = None
+        E.PARALLEL_BACKWARD = True
         launched = L.lib().pn_launch_count() - n0
         if graph["g"] is not None and not profile:
             launched = graph["launches"] * k

@@ -355,17 +355,17 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
             g_params.append([torch.zeros_like(t) for t in p.params] if want_w[i] else None)
         return g_grids, g_pts, g_params
     ps = pts.struct()
-    st = C.c_void_p(L.stream_ptr(device))
     mb = host_bound(plan.mask_bound) if plan.mask_bound is not None else None
     apply_mask = 1 if mb is not None else 0
-    with L.device_guard(device):
-        for i, p in enumerate(plan.passes):
+
+    def run_pass(i, p):
+            st = C.c_void_p(L.stream_ptr(device))      # the stream that is current for THIS pass
             nb = host_bound(p.norm_bound)
             gg = g_grids.get(p.grid_a) if p.grid_a else None
             if p.kind == "imap":
                 from . import imap
                 g_params.append(imap.backward(p, pts, g_raw, stashes[i], g_pts, plan.mask_bound, device, bool(want_w[i])))
-                continue
+                return
             ws = wst = None
             if want_w[i]:
                 f32 = dict(dtype=torch.float32, device=device)
@@ -415,7 +415,37 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                     g_params.append(gp)
                 else:
                     g_params.append(None)
+
+    # The passes of a stage are independent given g_raw (each writes its own grid and parameter gradients; the point
+    # gradient is accumulated with atomics), so the first pass (+ its weight gradients) runs on the current stream and
+    # the others on a side stream: as the persistent CTAs of one kernel drain, the CTAs of the other chain take the SMs.
+    side = _side_stream(device) if (PARALLEL_BACKWARD and len(plan.passes) > 1 and
+                                    all(p.kind != "imap" for p in plan.passes)) else None
+    with L.device_guard(device):
+        main = torch.cuda.current_stream(device)
+        if side is not None:
+            side.wait_stream(main)
+        for i, p in enumerate(plan.passes):
+            if side is not None and i >= 1:
+                with torch.cuda.stream(side):
+                    run_pass(i, p)
+            else:
+                run_pass(i, p)
+        if side is not None:
+            main.wait_stream(side)
     return g_grids, g_pts, g_params
+
+
+PARALLEL_BACKWARD = True
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return _SIDE_STREAMS[idx]
 
 
 # Optional callback ``hook(key, grad)`` fired from inside the backward as soon as a gradient
