@@ -204,9 +204,9 @@ def run_ours(args):
     ar_mode = os.environ.get("PN_BENCH_ALLREDUCE", "overlap")   # overlap | arena | nvls | simple
     arena = D.SymmetricGradArena(n_arena, dev) if (world > 1 and ar_mode == "nvls") else E.GradArena(n_arena, dev)
     E.GRAD_ARENA = arena
-    # SMs left to NCCL while gradient all-reduces are in flight (measured: N=8 1.72 -> 1.69 ms with 12-20; N=4 1.58 -> 1.60 ms
-    # with 16; N=2 no gain) -> only from 8 GPUs up by default
-    comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "16" if world >= 8 else "0"))
+    # SMs left to NCCL while gradient all-reduces are in flight: measured with the final kernels, N=8: 1.705 ms without,
+    # 1.728 ms with 16; N=4: 1.584 / 1.603 ms -> off by default
+    comm_sms = int(os.environ.get("PN_BENCH_COMM_SMS", "0"))
     reducer = D.OverlappedGradReducer(arena if ar_mode in ("arena", "nvls") else None, reserve_sms=comm_sms if world > 1 else 0)
 
     def h2d_inputs():   # host -> device copy of this step's inputs from pinned memory (e2e only)
@@ -309,9 +309,14 @@ def run_ours(args):
         pipe["i"] += 1
         return out
 
+    # two-stream backward: a gain on one GPU (1.28 -> 1.25 ms); with gradient all-reduces in flight it loses
+    # (N=8: 1.79 ms with, 1.705 ms without; N=2: 1.515 / 1.497 ms), so it is on only for world == 1
+    par_bwd = os.environ.get("PN_PARALLEL_BACKWARD", "1" if world == 1 else "0") != "0"
+    E.PARALLEL_BACKWARD = par_bwd
+
     def timed(k, e2e, profile):
         L.PROFILE = {} if profile else None
-        E.PARALLEL_BACKWARD = not profile   # per-kernel event times are taken with the backward passes one after another
+        E.PARALLEL_BACKWARD = (not profile) and par_bwd   # per-kernel event times: passes one after another
         evs = []
         if world > 1:
             dist.barrier()
@@ -335,7 +340,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         prof = L.PROFILE
         L.PROFILE = None
-        E.PARALLEL_BACKWARD = True
+        E.PARALLEL_BACKWARD = par_bwd
         launched = L.lib().pn_launch_count() - n0
         if graph["g"] is not None and not profile:
             launched = graph["launches"] * k

@@ -419,7 +419,9 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
     # The passes of a stage are independent given g_raw (each writes its own grid and parameter gradients; the point
     # gradient is accumulated with atomics), so the first pass (+ its weight gradients) runs on the current stream and
     # the others on a side stream: as the persistent CTAs of one kernel drain, the CTAs of the other chain take the SMs.
-    side = _side_stream(device) if (PARALLEL_BACKWARD and len(plan.passes) > 1 and
+    # (Not while a gradient-ready hook launches collectives from inside the backward: measured on 2 and 8 GPUs the
+    # two chains plus NCCL's kernels are slower than the serial order.)
+    side = _side_stream(device) if (PARALLEL_BACKWARD and GRAD_READY_HOOK is None and len(plan.passes) > 1 and
                                     all(p.kind != "imap" for p in plan.passes)) else None
     with L.device_guard(device):
         main = torch.cuda.current_stream(device)
@@ -436,7 +438,9 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
     return g_grids, g_pts, g_params
 
 
-PARALLEL_BACKWARD = True
+import os as _os
+
+PARALLEL_BACKWARD = _os.environ.get("PN_PARALLEL_BACKWARD", "1") != "0"   # two-stream backward (see plan_backward)
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
