@@ -103,7 +103,8 @@ typedef struct pn_stash {
 
 /* Scratch written by the input-gradient kernel for the weight-gradient kernel. */
 typedef struct pn_wscratch {
-  float* GA;   /* [5] planar-4 (N x 32): gradient at block pre-activations */
+  float* GA;   /* [5] planar-4 (N x 32): gradient at block pre-activations.  With the tensor-core engine and c_dim 32
+                * the backward leaves it unwritten: pn_grid_mlp_wgrad rebuilds it from GH and stash->relu_bits */
   float* GH;   /* [5] planar-4 (N x 32): gradient at block outputs */
   float* GARG; /* planar-4 (N x 96): gradient at the Fourier arguments */
   float* P32;  /* [3][N]: float32 points */
@@ -195,8 +196,10 @@ int pn_grid_mlp_bwd(const pn_points* pts, const pn_grid_mlp* w, const pn_grid* g
                     const double* norm_bound, const double* mask_bound, int apply_mask,
                     const float* g_raw, const pn_stash* stash, float* g_gridA, float* g_pts,
                     int accumulate_pts, const pn_wscratch* ws, void* stream);
-/* Weight gradients: sum over samples of (gradient x activation) outer products, as
- * tiled FFMA GEMMs over the stash/scratch; results atomically added into `g`. */
+/* Weight gradients: sum over samples of (gradient x activation) outer products over the stash / scratch written
+ * by pn_grid_mlp_fwd / _bwd of the SAME engine; results atomically added into `g` (NULL sinks are skipped).
+ * c_dim 32: one warp-specialised tcgen05 kernel for W, b, Wc, bc, Wo, bo and B (needs stash->relu_bits);
+ * c_dim 64: tcgen05 GEMM kernel + two small kernels; PN_MLP_ENGINE=ffma: tiled FFMA GEMMs. */
 int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash* stash, const pn_wscratch* ws,
                       const pn_grid_mlp_grad* g, void* stream);
 
