@@ -113,7 +113,10 @@ typedef struct pn_wscratch {
 
 enum { PN_OUT_SET_ALL = 0, /* raw[n] = (0,0,0,occ) or the 4 colour-decoder outputs */
        PN_OUT_SET_W = 1,   /* raw[n].w = occ, rgb kept */
-       PN_OUT_ADD_W = 2 }; /* raw[n].w += occ */
+       PN_OUT_ADD_W = 2,   /* raw[n].w += occ */
+       PN_OUT_SET_RGB = 3 }; /* raw[n].xyz = the colour-decoder outputs (n_out 4), w untouched.  SET_W / ADD_W touch only
+                              * the 4th float and SET_RGB only the first three, so the colour pass may run concurrently
+                              * (another stream) with the occupancy passes that fill w of the same buffer */
 
 const char* pn_last_error(void);
 int pn_version(void);

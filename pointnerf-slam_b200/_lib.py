@@ -57,7 +57,7 @@ class PnWscratch(C.Structure):
     _fields_ = [("GA", P), ("GH", P), ("GARG", P), ("P32", P), ("GO", P)]
 
 
-OUT_SET_ALL, OUT_SET_W, OUT_ADD_W = 0, 1, 2
+OUT_SET_ALL, OUT_SET_W, OUT_ADD_W, OUT_SET_RGB = 0, 1, 2, 3
 
 _lib: Optional[C.CDLL] = None
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pnslam.h")

@@ -54,6 +54,25 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+// One decoder result -> raw[n] according to out_mode (pnslam.h).  `force`: the point lies outside the mask bound.
+template <int NOUT>
+__device__ __forceinline__ void store_raw(float* __restrict__ raw, int64_t n, const float (&out)[4], int out_mode, bool force) {
+  float* r = raw + 4 * n;
+  if (NOUT == 4) {
+    if (out_mode == PN_OUT_SET_RGB) {
+      *reinterpret_cast<float2*>(r) = make_float2(out[0], out[1]);
+      r[2] = out[2];
+    } else {
+      *reinterpret_cast<float4*>(r) = make_float4(out[0], out[1], out[2], force ? 100.f : out[3]);
+    }
+  } else if (out_mode == PN_OUT_SET_ALL) {
+    *reinterpret_cast<float4*>(r) = make_float4(0.f, 0.f, 0.f, force ? 100.f : out[0]);
+  } else {
+    const float w = (out_mode == PN_OUT_ADD_W) ? r[3] + out[0] : out[0];
+    r[3] = force ? 100.f : w;
+  }
+}
+
 struct Bound6 {  // [lo_x hi_x lo_y hi_y lo_z hi_z]
   double v[6];
 };

@@ -280,19 +280,7 @@ __global__ void __launch_bounds__(kThreads, CD == 32 ? 2 : 1) k_grid_mlp_fwd(con
       for (int j = 0; j < 32; ++j) s = fmaf(wsm[OFF_WO + o * 32 + j], h[j], s);
       out[o] = s;
     }
-    if (valid) {
-      float4* r = reinterpret_cast<float4*>(a.raw) + n;
-      const bool force = a.apply_mask && !sp.inside;
-      if (NOUT == 4) {
-        *r = make_float4(out[0], out[1], out[2], force ? 100.f : out[3]);
-      } else {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.out_mode != PN_OUT_SET_ALL) v = *r;
-        v.w = (a.out_mode == PN_OUT_ADD_W) ? v.w + out[0] : out[0];
-        if (force) v.w = 100.f;
-        *r = v;
-      }
-    }
+    if (valid) store_raw<NOUT>(a.raw, n, out, a.out_mode, a.apply_mask && !sp.inside);
   }
 }
 
@@ -690,12 +678,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_coarse_fwd(const CoarseFwdArgs 
 #pragma unroll
     for (int j = 0; j < 32; ++j) out = fmaf(wsm[CO_WO + j], h[j], out);
     if (valid) {
-      float4* r = reinterpret_cast<float4*>(a.raw) + n;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.out_mode != PN_OUT_SET_ALL) v = *r;
-      v.w = (a.out_mode == PN_OUT_ADD_W) ? v.w + out : out;
-      if (a.apply_mask && !sp.inside) v.w = 100.f;
-      *r = v;
+      const float o4[4] = {out, 0.f, 0.f, 0.f};
+      store_raw<1>(a.raw, n, o4, a.out_mode, a.apply_mask && !sp.inside);
     }
   }
 }
@@ -816,6 +800,10 @@ extern "C" int pn_grid_mlp_fwd(const pn_points* pts, const pn_grid_mlp* w, const
     return 1;
   }
   if (apply_mask && !mask_bound) { set_error("pn_grid_mlp_fwd: apply_mask needs mask_bound"); return 1; }
+  if (out_mode < PN_OUT_SET_ALL || out_mode > PN_OUT_SET_RGB || (out_mode == PN_OUT_SET_RGB && w->n_out != 4)) {
+    set_error("pn_grid_mlp_fwd: bad out_mode %d for n_out %d", out_mode, w->n_out);
+    return 1;
+  }
   if (pts->N == 0) return 0;
   FwdArgs a;
   a.pts = *pts; a.w = make_mlp(w); a.ga = make_grid(gridA); a.gb = make_grid(gridB);
@@ -941,6 +929,7 @@ extern "C" int pn_coarse_mlp_fwd(const pn_points* pts, const pn_coarse_mlp* w, c
     set_error("pn_coarse_mlp_fwd: null grid/raw/bound");
     return 1;
   }
+  if (out_mode < PN_OUT_SET_ALL || out_mode > PN_OUT_ADD_W) { set_error("pn_coarse_mlp_fwd: bad out_mode %d", out_mode); return 1; }
   if (pts->N == 0) return 0;
   CoarseFwdArgs a;
   a.pts = *pts; a.w = make_coarse(w); a.g = make_grid(grid);

@@ -242,17 +242,7 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
       if (valid) {
         if (BITS) a.relu_bits[(int64_t)4 * N + n] = bits;
         if (a.H) store_planar32(a.H + (int64_t)4 * 32 * N, N, n, h);
-        float4* r = reinterpret_cast<float4*>(a.raw) + n;
-        const bool force = a.apply_mask && !sp.inside;
-        if (NOUT == 4) {
-          *r = make_float4(out[0], out[1], out[2], force ? 100.f : out[3]);
-        } else {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.out_mode != PN_OUT_SET_ALL) v = *r;
-          v.w = (a.out_mode == PN_OUT_ADD_W) ? v.w + out[0] : out[0];
-          if (force) v.w = 100.f;
-          *r = v;
-        }
+        store_raw<NOUT>(a.raw, n, out, a.out_mode, a.apply_mask && !sp.inside);
       }
     }
     // this tile's TMEM reads (tcgen05.wait::ld) are ordered before the next tile's MMAs by the

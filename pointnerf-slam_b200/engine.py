@@ -96,8 +96,9 @@ def _dec_bound(dec, default):
 
 def stage_passes(decoders, stage: str, default_bound) -> List[Pass]:
     """Kernel passes that realise NICE.forward for a stage (decoder.py:312-342).
-    The colour decoder runs first so that the occupancy passes can overwrite /
-    accumulate the 4th component exactly as ``raw[..., -1] = fine + middle``."""
+    In stage colour the colour decoder writes only raw[..., :3] and the occupancy passes only
+    raw[..., 3] (set by fine, then ``+= middle``: ``raw[..., -1] = fine + middle``), so the colour
+    pass is independent of the other two and may run on another stream (plan_forward)."""
     if stage == "coarse":
         d = decoders.coarse_decoder
         return [Pass("coarse", d, "grid_coarse", None, L.OUT_SET_ALL, _dec_bound(d, default_bound))]
@@ -111,7 +112,7 @@ def stage_passes(decoders, stage: str, default_bound) -> List[Pass]:
         return [p_fine(L.OUT_SET_ALL), p_mid(L.OUT_ADD_W)]
     if stage == "color":
         col = decoders.color_decoder
-        return [Pass("grid", col, "grid_color", None, L.OUT_SET_ALL, _dec_bound(col, default_bound)),
+        return [Pass("grid", col, "grid_color", None, L.OUT_SET_RGB, _dec_bound(col, default_bound)),
                 p_fine(L.OUT_SET_W), p_mid(L.OUT_ADD_W)]
     raise ValueError(f"unknown stage {stage!r}")
 
@@ -310,17 +311,19 @@ def plan_forward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, dev
     lib = L.lib()
     n = pts.n
     raw = torch.empty((n, 4), dtype=torch.float32, device=device)
-    stashes: List[Optional[Stash]] = []
     if n == 0:
         return raw, [None] * len(plan.passes)
     ps = pts.struct()
-    st = C.c_void_p(L.stream_ptr(device))
     mb = host_bound(plan.mask_bound) if plan.mask_bound is not None else None
     apply_mask = 1 if mb is not None else 0
-    with L.device_guard(device):
-        for i, p in enumerate(plan.passes):
-            stash = Stash(p, n, device, bool(want_w[i])) if (save and p.kind != "imap") else None
-            stashes.append(stash)
+    # everything that outlives this call is allocated here, on the caller's stream (a buffer allocated while a side
+    # stream is current would return to that stream's pool while kernels of the caller's stream may still use it)
+    stashes: List[Optional[Stash]] = [Stash(p, n, device, bool(want_w[i])) if (save and p.kind != "imap") else None
+                                      for i, p in enumerate(plan.passes)]
+
+    def run_pass(i, p):
+            st = C.c_void_p(L.stream_ptr(device))      # the stream that is current for THIS pass
+            stash = stashes[i]
             sst = stash.struct() if stash is not None else None
             nb = host_bound(p.norm_bound)
             if p.kind == "grid":
@@ -336,7 +339,23 @@ def plan_forward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, dev
                                               C.c_void_p(raw.data_ptr()), _byref(sst), st), "pn_coarse_mlp_fwd")
             else:
                 from . import imap
-                stashes[-1] = imap.forward(p, pts, raw, plan.mask_bound, device, save, bool(want_w[i]))
+                stashes[i] = imap.forward(p, pts, raw, plan.mask_bound, device, save, bool(want_w[i]))
+
+    # The colour pass (SET_RGB) and the occupancy passes write disjoint components of raw, so with PARALLEL_FORWARD the
+    # colour pass goes to a side stream (the two chains could fill each other's tails; see the flag for what was measured).
+    side = _side_stream(device) if (PARALLEL_FORWARD and any(p.out_mode == L.OUT_SET_RGB for p in plan.passes)) else None
+    with L.device_guard(device):
+        main = torch.cuda.current_stream(device)
+        if side is not None:
+            side.wait_stream(main)
+        for i, p in enumerate(plan.passes):
+            if side is not None and p.out_mode == L.OUT_SET_RGB:
+                with torch.cuda.stream(side):
+                    run_pass(i, p)
+            else:
+                run_pass(i, p)
+        if side is not None:
+            main.wait_stream(side)
     return raw, stashes
 
 
@@ -357,6 +376,8 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
     ps = pts.struct()
     mb = host_bound(plan.mask_bound) if plan.mask_bound is not None else None
     apply_mask = 1 if mb is not None else 0
+    # gradient sinks outlive this call: allocated here, on the caller's stream (see plan_forward)
+    sinks = [zeros_like_flat(p.params) if (want_w[i] and p.kind != "imap") else None for i, p in enumerate(plan.passes)]
 
     def run_pass(i, p):
             st = C.c_void_p(L.stream_ptr(device))      # the stream that is current for THIS pass
@@ -383,7 +404,7 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                 if GRAD_READY_HOOK is not None and gg is not None:
                     GRAD_READY_HOOK(p.grid_a, gg)          # this grid's gradient is final (one pass writes each grid)
                 if want_w[i]:
-                    gp = zeros_like_flat(p.params)
+                    gp = sinks[i]
                     g = L.PnGridMlpGrad()
                     g.B = gp[0].data_ptr()
                     for k in range(5):
@@ -405,7 +426,7 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                                               C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
                                               C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_coarse_mlp_bwd")
                 if want_w[i]:
-                    gp = zeros_like_flat(p.params)
+                    gp = sinks[i]
                     g = L.PnCoarseMlpGrad()
                     for k in range(5):
                         g.W[k] = gp[k].data_ptr(); g.b[k] = gp[5 + k].data_ptr()
@@ -441,6 +462,9 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
 import os as _os
 
 PARALLEL_BACKWARD = _os.environ.get("PN_PARALLEL_BACKWARD", "1") != "0"   # two-stream backward (see plan_backward)
+# colour pass beside the occupancy passes: possible (disjoint components of raw) but measured without gain on a B200
+# (mapping 1.25 ms, tracking 0.31 ms either way; +0.1 ms of host time in eager mode), so off by default
+PARALLEL_FORWARD = _os.environ.get("PN_PARALLEL_FORWARD", "0") != "0"
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
