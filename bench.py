@@ -394,8 +394,8 @@ def run_ours(args):
     # gradient, the output gradient and the point (160 + 96 + 32 + 160 + 96 + 4 + 3 floats per sample) + 20 B of ReLU masks
     alg_wgrad = n_samples * ((160 + 96 + 32 + 160 + 96 + 4 + 3) * 4 + 20)
     # measured DRAM traffic per launch of the same kernels (ncu --set full, profiles/r1_dram_traffic_per_launch.json)
-    ncu_name = {"grid_mlp_fwd:color": "k_grid_mlp_fwd_tc<32, 4>", "grid_mlp_fwd:fine": "k_grid_mlp_fwd_tc<64, 1>",
-                "grid_mlp_fwd:middle": "k_grid_mlp_fwd_tc<32, 1>", "grid_mlp_bwd:color": "k_grid_mlp_bwd_tc<32, 4, 1, 1, 1>",
+    ncu_name = {"grid_mlp_fwd:color": "k_grid_mlp_fwd_tc<32, 4, 1>", "grid_mlp_fwd:fine": "k_grid_mlp_fwd_tc<64, 1, 1>",
+                "grid_mlp_fwd:middle": "k_grid_mlp_fwd_tc<32, 1, 1>", "grid_mlp_bwd:color": "k_grid_mlp_bwd_tc<32, 4, 1, 1, 1>",
                 "grid_mlp_bwd:fine": "k_grid_mlp_bwd_tc<64, 1, 1, 1, 0>", "grid_mlp_bwd:middle": "k_grid_mlp_bwd_tc<32, 1, 1, 1, 0>",
                 "grid_mlp_wgrad:color": "k_wgrad_tc"}
     traffic = None
