@@ -8,6 +8,7 @@ edges only.
 from __future__ import annotations
 
 import ctypes as C
+import os as _os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -390,8 +391,11 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
             ws = wst = None
             if want_w[i]:
                 f32 = dict(dtype=torch.float32, device=device)
-                ws = dict(GA=torch.empty(5 * 32 * n, **f32), GH=torch.empty(5 * 32 * n, **f32),
-                          GARG=torch.empty(96 * n, **f32), P32=torch.empty(3 * n, **f32), GO=torch.empty(4 * n, **f32))
+                ws = dict(GH=torch.empty(5 * 32 * n, **f32), GARG=torch.empty(96 * n, **f32),
+                          P32=torch.empty(3 * n, **f32), GO=torch.empty(4 * n, **f32))
+                # GA is neither written nor read by the tensor-core engine for c_dim 32 (pnslam.h, pn_wscratch): alias it
+                tc32 = p.kind == "grid" and p.c_dim == 32 and _os.environ.get("PN_MLP_ENGINE", "")[:1] != "f"
+                ws["GA"] = ws["GH"] if tc32 else torch.empty(5 * 32 * n, **f32)
                 wst = L.PnWscratch(*[ws[k].data_ptr() for k in ("GA", "GH", "GARG", "P32", "GO")])
             sst = stashes[i].struct()
             if p.kind == "grid":
@@ -458,8 +462,6 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
             main.wait_stream(side)
     return g_grids, g_pts, g_params
 
-
-import os as _os
 
 PARALLEL_BACKWARD = _os.environ.get("PN_PARALLEL_BACKWARD", "1") != "0"   # two-stream backward (see plan_backward)
 # colour pass beside the occupancy passes: possible (disjoint components of raw) but measured without gain on a B200
