@@ -96,3 +96,14 @@ def test_header_prototypes_cover_every_entry_point():
         assert fn.argtypes is not None, name
     with pytest.raises(Exception):
         lib.pn_reserve_sms()          # wrong argument count
+
+
+def test_reserve_sms_round_trip():
+    """pn_reserve_sms returns the previous reservation and clamps negatives (no device needed)."""
+    lib = L.lib()
+    prev = lib.pn_reserve_sms(12)
+    try:
+        assert lib.pn_reserve_sms(-5) == 12      # negative -> 0
+        assert lib.pn_reserve_sms(0) == 0
+    finally:
+        lib.pn_reserve_sms(prev)
