@@ -268,6 +268,15 @@ int pn_points_to_rays_bwd(const float* g_pts, const double* z, int64_t R, int S,
 int pn_mapping_loss(const double* depth, const float* color, const float* gt_depth, const float* gt_color, int64_t R,
                     int use_color, float w_color, double* loss, double* g_depth, float* g_color, void* stream);
 
+/* Tracker loss head (src/Tracker.py:306-330): tmp = |gt_depth - depth| / sqrt(var + 1e-10) (float64);
+ * mask = gt_depth > 0, and with handle_dynamic also tmp < 10 * median(tmp) (torch.median: rank (R-1)/2);
+ * loss = sum_mask tmp (+ w_color * sum_mask |gt_color - color| when use_color).  Also its gradient w.r.t. depth
+ * (R, float64) and colour (R,3, float32, scaled by w_color); var is treated as detached, as in the reference.
+ * One CTA, deterministic; R <= 8192 (the reference tracks 200-5000 pixels). */
+int pn_tracking_loss(const double* depth, const double* var, const float* color, const float* gt_depth,
+                     const float* gt_color, int64_t R, int handle_dynamic, int use_color, float w_color, double* loss,
+                     double* g_depth, float* g_color, void* stream);
+
 /* tcgen05 self-test: Y (128,32) = X (128,K) . W (32,K)^T through the 3xTF32 tensor-core path
  * (operands in shared memory, accumulator in tensor memory); K multiple of 8, <= 128. */
 int pn_tc_selftest(const float* X, const float* W, float* Y, int K, void* stream);

@@ -12,7 +12,7 @@ Modules
   common    get_samples / get_rays / get_camera_from_tensor / ...  (src/common.py)
   config    get_model / load_bound / grid_init  (src/config.py, src/NICE_SLAM.py)
   dist      ray sharding + NCCL gradient all-reduce for the mapping step
-  losses    mapping_loss: the Mapper's loss head and its gradient in one launch (src/Mapper.py:628-646)
+  losses    mapping_loss / tracking_loss: the Mapper's and Tracker's loss heads with their gradients, one launch each
   graphs    GraphedStep: one tracking / mapping iteration captured in a CUDA graph
   csrc/     CUDA kernels (sm_100a) and the C ABI
 """

@@ -670,6 +670,81 @@ __global__ void __launch_bounds__(1024) k_mapping_loss(const double* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Tracker loss head (src/Tracker.py:306-330) with its gradient, one launch, one CTA.
+//   tmp  = |gt_depth - depth| / sqrt(var + 1e-10)                      (float64)
+//   mask = gt_depth > 0  [ & tmp < 10 * median(tmp)  when handle_dynamic ]
+//   loss = sum_mask tmp + w_color * sum_mask |gt_color - color|
+// torch.median of n values is the element of rank (n-1)/2: tmp is sorted in shared memory (bitonic, padded with
+// +inf to a power of two), so R <= kTrackMaxRays.  Fixed summation order: deterministic.
+// ---------------------------------------------------------------------------
+constexpr int kTrackMaxRays = 8192;
+
+__global__ void __launch_bounds__(1024) k_tracking_loss(const double* __restrict__ depth, const double* __restrict__ var,
+                                                        const float* __restrict__ color, const float* __restrict__ gt_depth,
+                                                        const float* __restrict__ gt_color, int R, int handle_dynamic,
+                                                        int use_color, float w_color, double* __restrict__ loss,
+                                                        double* __restrict__ g_depth, float* __restrict__ g_color) {
+  extern __shared__ double srt[];
+  __shared__ double red_d[32], red_c[32];
+  __shared__ double thr_s;
+  const int tid = threadIdx.x;
+  double thr = 0.0;
+  if (handle_dynamic) {
+    int P2 = 1;
+    while (P2 < R) P2 <<= 1;
+    for (int r = tid; r < P2; r += blockDim.x)
+      srt[r] = r < R ? __ddiv_rn(fabs((double)gt_depth[r] - depth[r]), __dsqrt_rn(__dadd_rn(var[r], 1e-10))) : __longlong_as_double(0x7ff0000000000000LL);
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P2; i += blockDim.x) {
+          const int l = i ^ j;
+          if (l > i) {
+            const double a = srt[i], b = srt[l];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { srt[i] = b; srt[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) thr_s = __dmul_rn(10.0, srt[(R - 1) / 2]);
+    __syncthreads();
+    thr = thr_s;
+  }
+  double sd = 0.0, sc = 0.0;
+  for (int r = tid; r < R; r += blockDim.x) {
+    const float g = gt_depth[r];
+    const double diff = (double)g - depth[r];
+    const double inv = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(var[r], 1e-10)));
+    const double t = __ddiv_rn(fabs(diff), __dsqrt_rn(__dadd_rn(var[r], 1e-10)));
+    const bool m = (g > 0.f) && (!handle_dynamic || t < thr);
+    if (m) sd += t;
+    // d(|gt - depth| / s)/d depth = -sign(gt - depth) / s
+    g_depth[r] = m ? (diff > 0.0 ? -inv : (diff < 0.0 ? inv : 0.0)) : 0.0;
+    if (use_color) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float dc = __fsub_rn(gt_color[3 * r + a], color[3 * r + a]);
+        if (m) sc += (double)fabsf(dc);
+        g_color[3 * r + a] = m ? (dc > 0.f ? -w_color : (dc < 0.f ? w_color : 0.f)) : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sd += __shfl_xor_sync(kFull, sd, o); sc += __shfl_xor_sync(kFull, sc, o); }
+  if ((tid & 31) == 0) { red_d[tid >> 5] = sd; red_c[tid >> 5] = sc; }
+  __syncthreads();
+  if (tid < 32) {
+    sd = tid < (blockDim.x >> 5) ? red_d[tid] : 0.0;
+    sc = tid < (blockDim.x >> 5) ? red_c[tid] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sd += __shfl_xor_sync(kFull, sd, o); sc += __shfl_xor_sync(kFull, sc, o); }
+    if (tid == 0) *loss = use_color ? sd + (double)__fmul_rn(w_color, (float)sc) : sd;
+  }
+}
+
 }  // namespace
 }  // namespace pn
 
@@ -820,6 +895,22 @@ extern "C" int pn_grid_transpose(const float* src, float* dst, int D, int H, int
   const int64_t V = (int64_t)D * H * W;
   k_grid_transpose<<<(unsigned)((V + 31) / 32), 256, 0, PN_ST>>>(src, dst, V, to_channels_last);
   return launch_status("k_grid_transpose");
+}
+
+extern "C" int pn_tracking_loss(const double* depth, const double* var, const float* color, const float* gt_depth,
+                                const float* gt_color, int64_t R, int handle_dynamic, int use_color, float w_color, double* loss,
+                                double* g_depth, float* g_color, void* stream) {
+  if (!depth || !var || !gt_depth || !loss || !g_depth || R < 1 || (use_color && (!color || !gt_color || !g_color))) {
+    set_error("pn_tracking_loss: bad arguments");
+    return 1;
+  }
+  if (R > pn::kTrackMaxRays) { set_error("pn_tracking_loss: at most %d rays", pn::kTrackMaxRays); return 1; }
+  size_t sm = 0;
+  if (handle_dynamic) { size_t p2 = 1; while ((int64_t)p2 < R) p2 <<= 1; sm = p2 * sizeof(double); }
+  cudaFuncSetAttribute(pn::k_tracking_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pn::kTrackMaxRays * sizeof(double)));
+  pn::k_tracking_loss<<<1, 1024, sm, PN_ST>>>(depth, var, color, gt_depth, gt_color, (int)R, handle_dynamic, use_color, w_color, loss,
+                                             g_depth, g_color);
+  return launch_status("k_tracking_loss");
 }
 
 extern "C" int pn_mapping_loss(const double* depth, const float* color, const float* gt_depth, const float* gt_color, int64_t R,

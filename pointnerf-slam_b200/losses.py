@@ -56,3 +56,56 @@ def mapping_loss(depth: torch.Tensor, color: Optional[torch.Tensor], gt_depth: t
     use_color = ((not nice) or stage == "color") and color is not None and gt_color is not None
     return _MappingLossFn.apply(depth, color if use_color else None, gt_depth, gt_color if use_color else None,
                                 float(w_color), bool(use_color))
+
+
+class _TrackingLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, var, color, gt_depth, gt_color, w_color, use_color, handle_dynamic):
+        dev = depth.device
+        d = depth.detach().double().contiguous()
+        v = var.detach().double().contiguous()
+        gd = gt_depth.detach().float().contiguous()
+        R = d.shape[0]
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        g_depth = torch.empty(R, dtype=torch.float64, device=dev)
+        c = gc = g_color = None
+        if use_color:
+            c = color.detach().float().contiguous()
+            gc = gt_color.detach().float().contiguous()
+            g_color = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        with L.device_guard(dev):
+            L.check(L.lib().pn_tracking_loss(C.c_void_p(d.data_ptr()), C.c_void_p(v.data_ptr()), C.c_void_p(L.ptr(c)),
+                                             C.c_void_p(gd.data_ptr()), C.c_void_p(L.ptr(gc)), C.c_int64(R), int(handle_dynamic),
+                                             int(use_color), C.c_float(w_color), C.c_void_p(loss.data_ptr()),
+                                             C.c_void_p(g_depth.data_ptr()), C.c_void_p(L.ptr(g_color)),
+                                             C.c_void_p(L.stream_ptr(dev))), "pn_tracking_loss")
+        ctx.save_for_backward(g_depth, g_color)
+        ctx.color_dtype = color.dtype if use_color else None
+        ctx.depth_dtype = depth.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        g_depth, g_color = ctx.saved_tensors
+        gd = (g_depth * go).to(ctx.depth_dtype) if ctx.needs_input_grad[0] else None
+        gc = (g_color * go).to(ctx.color_dtype) if (g_color is not None and ctx.needs_input_grad[2]) else None
+        return gd, None, gc, None, None, None, None, None
+
+
+TRACKING_LOSS_MAX_RAYS = 8192
+
+
+def tracking_loss(depth: torch.Tensor, uncertainty: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
+                  gt_color: Optional[torch.Tensor], w_color: float = 0.5, use_color: bool = True,
+                  handle_dynamic: bool = True) -> torch.Tensor:
+    """Tracker.py:306-330: uncertainty-weighted masked L1 depth loss (the uncertainty is detached; with
+    ``handle_dynamic`` rays whose weighted residual exceeds ten times the median are dropped) plus ``w_color`` times the
+    masked L1 colour loss.  Value and gradient come from one launch (the reference spends ~28 elementwise, reduction
+    and sort launches on it, forward and backward).  Returns a float64 scalar."""
+    if not depth.is_cuda:
+        raise RuntimeError("pointnerf_slam_b200.losses.tracking_loss needs CUDA tensors (there is no CPU path)")
+    if depth.shape[0] > TRACKING_LOSS_MAX_RAYS or depth.shape[0] == 0:
+        raise ValueError(f"tracking_loss handles 1..{TRACKING_LOSS_MAX_RAYS} rays per call (got {depth.shape[0]})")
+    use_color = bool(use_color) and color is not None and gt_color is not None
+    return _TrackingLossFn.apply(depth, uncertainty, color if use_color else None, gt_depth, gt_color if use_color else None,
+                                 float(w_color), use_color, bool(handle_dynamic))

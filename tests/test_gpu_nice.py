@@ -312,3 +312,30 @@ def test_mapping_loss_head_matches_oracle(stage):
         assert cc.grad is None
     again = P.losses.mapping_loss(dd, cc, gt_depth.cuda(), gt_color.cuda(), stage, 0.2)
     assert again.item() == out.item(), "fixed summation order: run-to-run deterministic"
+
+
+@pytest.mark.parametrize("handle_dynamic,R", [(True, 1000), (False, 1000), (True, 203), (True, 5000)])
+def test_tracking_loss_head_matches_oracle(handle_dynamic, R):
+    """losses.tracking_loss (Tracker.py:306-330): value, median-based mask and gradients vs the oracle's torch expression."""
+    import pointnerf_slam_b200 as P
+    g = torch.Generator().manual_seed(21 + R)
+    depth = (1.0 + torch.rand(R, generator=g, dtype=torch.float64)).requires_grad_(True)
+    var = 1e-3 + 0.1 * torch.rand(R, generator=g, dtype=torch.float64)
+    color = torch.rand(R, 3, generator=g).requires_grad_(True)
+    gt_depth = (depth.detach() + 0.05 * torch.randn(R, generator=g, dtype=torch.float64)).float()
+    gt_depth[torch.rand(R, generator=g) < 0.1] = 0.0
+    big = torch.rand(R, generator=g) < 0.05            # outliers that the median test must drop
+    gt_depth[big] += 3.0
+    gt_color = torch.rand(R, 3, generator=g)
+    ref = O.tracking_loss(depth, var, color, gt_depth, gt_color, 0.5, handle_dynamic)
+    (2.0 * ref).backward()
+    dd = depth.detach().cuda().requires_grad_(True)
+    cc = color.detach().cuda().requires_grad_(True)
+    out = P.losses.tracking_loss(dd, var.cuda(), cc, gt_depth.cuda(), gt_color.cuda(), 0.5, True, handle_dynamic)
+    assert out.dtype == torch.float64 and out.dim() == 0
+    (2.0 * out).backward()
+    assert abs(out.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    torch.testing.assert_close(dd.grad.cpu(), depth.grad, rtol=1e-14, atol=0)
+    torch.testing.assert_close(cc.grad.cpu(), color.grad, rtol=0, atol=0)
+    if handle_dynamic:
+        assert int((dd.grad == 0).sum()) > int((gt_depth == 0).sum()), "the median test must have dropped outliers"

@@ -61,6 +61,22 @@ ms = timeit(gstep, 50)
 out["tracking_1000px_fwd_bwd_pose_cuda_graph"] = {"ms_per_iter": round(ms, 4), "rays_per_s": round(1000 / ms * 1e3, 1),
                                                    "library_kernels_per_replay": gstep.launches}
 gstep.release()
+# ... and with the package's fused tracker loss head (losses.tracking_loss, handle_dynamic as in the shipped configs)
+def tracking_fused():
+    c = P.get_camera_from_tensor(cam)
+    o, d, gd, gc = P.get_samples(100, B.H - 100, 100, B.W - 100, 1000, B.H, B.W, B.FX, B.FY, B.CX, B.CY, c, depth, color, dev)
+    dd, vv, cc = r.render_batch_ray(grids, model, d, o, dev, "color", gt_depth=gd)
+    loss = P.losses.tracking_loss(dd, vv, cc, gd, gc, 0.5, True, True)
+    cam.grad = None
+    loss.backward()
+    return loss
+ms = timeit(tracking_fused, 50)
+out["tracking_1000px_fused_loss_eager"] = {"ms_per_iter": round(ms, 4), "rays_per_s": round(1000 / ms * 1e3, 1)}
+gstep = P.graphs.GraphedStep(tracking_fused)
+ms = timeit(gstep, 50)
+out["tracking_1000px_fused_loss_cuda_graph"] = {"ms_per_iter": round(ms, 4), "rays_per_s": round(1000 / ms * 1e3, 1),
+                                                 "library_kernels_per_replay": gstep.launches}
+gstep.release()
 r.freeze_map = False
 
 # ---- [5a] dense render
