@@ -76,6 +76,9 @@ def test_cuda_only_entry_points_fail_loudly_on_cpu():
         P.graphs.GraphedStep(lambda: torch.zeros(()))
     with pytest.raises(RuntimeError):
         P.losses.mapping_loss(torch.zeros(4, dtype=torch.float64), torch.zeros(4, 3), torch.ones(4), torch.zeros(4, 3))
+    with pytest.raises(RuntimeError):
+        P.losses.tracking_loss(torch.zeros(4, dtype=torch.float64), torch.ones(4, dtype=torch.float64), torch.zeros(4, 3),
+                               torch.ones(4), torch.zeros(4, 3))
     dec = _decoders()
     slam = types.SimpleNamespace(bound=torch.tensor([[-1.0, 1.0]] * 3), H=8, W=8, fx=8.0, fy=8.0, cx=3.5, cy=3.5, nice=True)
     cfg = {"rendering": {"lindisp": False, "perturb": 0.0, "N_samples": 4, "N_surface": 2, "N_importance": 0}, "scale": 1,
