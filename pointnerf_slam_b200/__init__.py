@@ -1,16 +1,21 @@
-"""Importable name of the package that lives in ``pointnerf-slam_b200/``.
+"""B200-native differentiable ray-rendering path of pointNeRF-SLAM / NICE-SLAM.
 
-The product directory is named after the reference repository and contains a
-hyphen; this shim points ``__path__`` at it so that
-``import pointnerf_slam_b200.renderer`` etc. resolve to the real files.
+Import as ``pointnerf_slam_b200`` (``pointnerf-slam_b200`` at the repo root is a
+symbolic link to this directory: the name the project is known by, which Python
+cannot import because of the hyphen).
+
+Modules
+  _lib      ctypes binding of libpnslam.so (C ABI in include/pnslam.h)
+  engine    decoder passes, stashes, autograd boundaries
+  renderer  Renderer  (drop-in for src/utils/Renderer.py)
+  decoder   NICE / MLP / MLP_no_xyz  (drop-in for src/conv_onet/models/decoder.py)
+  common    get_samples / get_rays / get_camera_from_tensor / ...  (src/common.py)
+  config    get_model / load_bound / grid_init  (src/config.py, src/NICE_SLAM.py)
+  dist      ray sharding + NCCL gradient all-reduce for the mapping step
+  losses    mapping_loss / tracking_loss: the Mapper's and Tracker's loss heads with their gradients, one launch each
+  graphs    GraphedStep: one tracking / mapping iteration captured in a CUDA graph
+  csrc/     CUDA kernels (sm_100a) and the C ABI
 """
-import os as _os
-
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "pointnerf-slam_b200")
-if not _os.path.isdir(_real):
-    raise ImportError(f"package directory {_real} is missing")
-__path__.insert(0, _real)
-__doc__ = open(_os.path.join(_real, "__init__.py")).read().split('"""')[1]
 
 from . import _lib, engine, common, decoder, config, renderer, graphs, losses  # noqa: E402,F401
 from .renderer import Renderer  # noqa: E402,F401

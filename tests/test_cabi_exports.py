@@ -46,7 +46,7 @@ def test_product_path_refuses_cpu_tensors():
 
 
 def test_product_does_not_import_oracle():
-    pkg = os.path.join(ROOT, "pointnerf-slam_b200")
+    pkg = os.path.join(ROOT, "pointnerf_slam_b200")
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             txt = open(os.path.join(pkg, fn)).read()
