@@ -188,8 +188,10 @@ class OverlappedGradReducer:
             self.items.append((key, list(grad) if isinstance(grad, (list, tuple)) else grad, "arena" if in_arena else None, None))
             return
         if isinstance(grad, (list, tuple)):           # parameter gradients: views of one flat buffer
-            flat = grad[0]._base if grad[0]._base is not None else None
-            if flat is None or any(g._base is not flat for g in grad):
+            # engine.zeros_like_flat hands over the exact slice it carved (never ``_base``: with a gradient arena
+            # installed that is the whole arena, and reducing it would sum every other sink a second time)
+            flat = getattr(grad, "flat", None)
+            if flat is not None and not flat.is_contiguous():
                 flat = None
             if flat is not None:
                 work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)

@@ -486,15 +486,22 @@ def _side_stream(device) -> "torch.cuda.Stream":
 GRAD_READY_HOOK = None
 
 
-def zeros_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+class FlatGrads(list):
+    """Parameter-gradient views plus the exact flat slice they were carved from (``.flat``).  The slice, not
+    ``view._base``, is what a collective must reduce: with a GradArena installed ``_base`` is the WHOLE arena."""
+    flat: torch.Tensor
+
+
+def zeros_like_flat(tensors: Sequence[torch.Tensor]) -> "FlatGrads":
     """Zeroed gradient sinks for a list of parameters, carved out of ONE buffer (one
     memset launch instead of one per parameter; every view stays 16-byte aligned)."""
     sizes = [(t.numel() + 3) // 4 * 4 for t in tensors]
     flat = _zeros(sum(sizes), tensors[0].device)
-    out, off = [], 0
+    out, off = FlatGrads(), 0
     for t, sz in zip(tensors, sizes):
         out.append(flat[off:off + t.numel()].view(t.shape))
         off += sz
+    out.flat = flat
     return out
 
 

@@ -121,9 +121,33 @@ def _reducer_worker(rank, world, port, out):
         E.GRAD_READY_HOOK("grid_color", g2)
         E.GRAD_READY_HOOK(("params", "color"), gp2)
     red2.finish({"grid_color": leaf}, decoders={"color": dec})
-    E.GRAD_ARENA = None
     dist.all_reduce(e_grid); dist.all_reduce(e_p3)
     ok = ok and torch.allclose(leaf.grad, e_grid) and torch.allclose(params[3].grad, e_p3)
+    # bench.py's multi-GPU default: arena installed, per-gradient overlapped reductions (reducer WITHOUT the arena).
+    # Every sink is a view of a view of arena.buf; each must be summed exactly once.
+    arena.reset()
+    g3 = E.new_grid_grad(leaf); g3.copy_(torch.randn(g3.shape))
+    other = E.zeros((17, 3), "cpu"); other.copy_(torch.randn(17, 3))       # a sink no hook ever announces (g_pts)
+    gp3 = E.zeros_like_flat(params)
+    for t in gp3:
+        t.copy_(torch.randn(t.shape))
+    assert gp3[0]._base is arena.buf and gp3.flat.numel() < arena.buf.numel()
+    leaf.grad = g3
+    for p_, t in zip(params, gp3):
+        p_.grad = t
+    e_grid3, e_all = g3.clone(), [t.clone() for t in gp3]
+    keep_other = other.clone()
+    red3 = D.OverlappedGradReducer(None)
+    with red3:
+        E.GRAD_READY_HOOK("grid_color", g3)
+        E.GRAD_READY_HOOK(("params", "color"), gp3)
+    red3.finish({"grid_color": leaf}, decoders={"color": dec})
+    E.GRAD_ARENA = None
+    dist.all_reduce(e_grid3)
+    for t in e_all:
+        dist.all_reduce(t)
+    ok = ok and torch.allclose(leaf.grad, e_grid3) and all(torch.allclose(p_.grad, t) for p_, t in zip(params, e_all))
+    ok = ok and torch.equal(other, keep_other)                               # untouched by any collective
     if rank == 0:
         torch.save({"ok": bool(ok)}, out)
     dist.barrier()
