@@ -7,8 +7,9 @@
  * point names the reference lines whose ATen op chain it replaces.  All
  * pointers are DEVICE pointers unless stated; `stream` is a cudaStream_t.
  * Every function returns 0 on success, non-zero on error; pn_last_error()
- * returns a thread-local message.  The library keeps no global mutable state
- * and never caches caller pointers across calls.
+ * returns a thread-local message.  The library never caches caller pointers
+ * across calls; its only process-wide state is the launch counter
+ * (pn_launch_count) and the SM reservation (pn_reserve_sms).
  *
  * Layout conventions
  *   - feature grids are channels-last: [Z][Y][X][32] float32 (the memory of a
@@ -103,8 +104,8 @@ typedef struct pn_stash {
 
 /* Scratch written by the input-gradient kernel for the weight-gradient kernel. */
 typedef struct pn_wscratch {
-  float* GA;   /* [5] planar-4 (N x 32): gradient at block pre-activations.  With the tensor-core engine and c_dim 32
-                * the backward leaves it unwritten: pn_grid_mlp_wgrad rebuilds it from GH and stash->relu_bits */
+  float* GA;   /* [5] planar-4 (N x 32): gradient at block pre-activations.  For c_dim 32 the backward leaves it
+                * unwritten: pn_grid_mlp_wgrad rebuilds it from GH and stash->relu_bits */
   float* GH;   /* [5] planar-4 (N x 32): gradient at block outputs */
   float* GARG; /* planar-4 (N x 96): gradient at the Fourier arguments */
   float* P32;  /* [3][N]: float32 points */
@@ -202,7 +203,7 @@ int pn_grid_mlp_bwd(const pn_points* pts, const pn_grid_mlp* w, const pn_grid* g
 /* Weight gradients: sum over samples of (gradient x activation) outer products over the stash / scratch written
  * by pn_grid_mlp_fwd / _bwd of the SAME engine; results atomically added into `g` (NULL sinks are skipped).
  * c_dim 32: one warp-specialised tcgen05 kernel for W, b, Wc, bc, Wo, bo and B (needs stash->relu_bits);
- * c_dim 64: tcgen05 GEMM kernel + two small kernels; PN_MLP_ENGINE=ffma: tiled FFMA GEMMs. */
+ * c_dim 64: tcgen05 GEMM kernel + two small kernels (tiled FFMA GEMMs only when some W / b / Wc / bc sinks are NULL). */
 int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash* stash, const pn_wscratch* ws,
                       const pn_grid_mlp_grad* g, void* stream);
 
@@ -264,18 +265,24 @@ int pn_points_to_rays_bwd(const float* g_pts, const double* z, int64_t R, int S,
 /* -------- loss head of the mapping iteration (src/Mapper.py:628-646) -------- */
 /* loss = sum_{gt_depth>0} |gt_depth - depth|  (+ w_color * sum |gt_color - color| when use_color), float64 scalar;
  * also its gradient: g_depth (R) float64, g_color (R,3) float32 (already scaled by w_color).  One CTA with a fixed
- * summation order (deterministic); the colour sum is rounded to float32 before scaling, as in the reference. */
+ * summation order (deterministic); the colour sum is rounded to float32 before scaling, as in the reference.
+ * depth_supervision == 0 selects the fork's colour-only branch (Mapper.py:633-637): loss = sum |gt_color - color|
+ * (unweighted), no depth gradient. */
 int pn_mapping_loss(const double* depth, const float* color, const float* gt_depth, const float* gt_color, int64_t R,
-                    int use_color, float w_color, double* loss, double* g_depth, float* g_color, void* stream);
+                    int use_color, float w_color, int depth_supervision, double* loss, double* g_depth, float* g_color,
+                    void* stream);
 
 /* Tracker loss head (src/Tracker.py:306-330): tmp = |gt_depth - depth| / sqrt(var + 1e-10) (float64);
- * mask = gt_depth > 0, and with handle_dynamic also tmp < 10 * median(tmp) (torch.median: rank (R-1)/2);
+ * mask = gt_depth > 0, and with handle_dynamic also tmp < 10 * median(tmp) (torch.median: rank (R-1)/2; a NaN in tmp
+ * makes the median NaN and the mask empty, as in torch);
  * loss = sum_mask tmp (+ w_color * sum_mask |gt_color - color| when use_color).  Also its gradient w.r.t. depth
  * (R, float64) and colour (R,3, float32, scaled by w_color); var is treated as detached, as in the reference.
- * One CTA, deterministic; R <= 8192 (the reference tracks 200-5000 pixels). */
+ * depth_supervision == 0: the fork's colour-only branch (Tracker.py:313-318): loss = sum_mask |gt_color - color|.
+ * One CTA, deterministic.  R <= 8192: tmp is sorted in shared memory; larger R (the fork tracker can pass every
+ * pixel with depth): the median comes from an 8-pass radix select over the bit patterns. */
 int pn_tracking_loss(const double* depth, const double* var, const float* color, const float* gt_depth,
-                     const float* gt_color, int64_t R, int handle_dynamic, int use_color, float w_color, double* loss,
-                     double* g_depth, float* g_color, void* stream);
+                     const float* gt_color, int64_t R, int handle_dynamic, int use_color, float w_color,
+                     int depth_supervision, double* loss, double* g_depth, float* g_color, void* stream);
 
 /* tcgen05 self-test: Y (128,32) = X (128,K) . W (32,K)^T through the 3xTF32 tensor-core path
  * (operands in shared memory, accumulator in tensor memory); K multiple of 8, <= 128. */
@@ -284,6 +291,85 @@ int pn_tc_selftest(const float* X, const float* W, float* Y, int K, void* stream
  * which of LBO / SBO is the stride between core matrices along K.  On sm_100a kind::tf32 returns zeros for both
  * conventions with the no-swizzle layout, which is why the weight-gradient kernels transpose in shared memory. */
 int pn_tc_selftest_mn(const float* Xt, const float* Wt, float* Y, int K, int swap, void* stream);
+
+/* ======== callers either side of the rendering path ======== */
+
+/* -------- frustum feature selection (src/Mapper.py:129-200, Mapper.get_mask_from_c2w) --------
+ * xs / ys / zs: device float32 axes of the voxel lattice (the host's torch.linspace(bound[a][0], bound[a][1], n),
+ * Mapper.py:145-147); w2c_host: HOST float32[16], row-major np.linalg.inv(c2w) (Mapper.py:154); cam_o_host: HOST
+ * float32[3] = c2w[:3,3].  depth_img: device (H,W) float32.  The depth of a voxel is cv2.remap(INTER_LINEAR) of the
+ * image at its projection (5-bit fixed-point coordinates, zero border); voxels whose remapped depth is 0 take the
+ * maximum over all voxels (Mapper.py:180-181).  scratch_depth: nx*ny*nz floats; scratch_max: 1 float.
+ * mask: uint8 [nz][ny][nx] (the memory order of the channels-last grid), 1 = optimise this voxel. */
+int pn_frustum_mask(const float* xs, int nx, const float* ys, int ny, const float* zs, int nz, const float* w2c_host,
+                    const float* cam_o_host, double fx, double fy, double cx, double cy, int H, int W,
+                    const float* depth_img, float* scratch_depth, float* scratch_max, uint8_t* mask, void* stream);
+
+/* -------- optimiser step (src/Mapper.py:482-505, 529-536, 657-674; configs/nice_slam.yaml:71-95) --------
+ * torch.optim.Adam (no weight decay, no amsgrad) over a table of tensors in ONE launch.  `table`: device array of
+ * `ntensors` rows {float* p; const float* g; float* m; float* v; const uint8_t* mask; int64_t n; int32_t row;
+ * int32_t group; int64_t block0} (64 bytes each; g == NULL: tensor skipped, as Adam skips parameters without
+ * gradient).  mask (optional): one byte per `row` consecutive elements; elements whose byte is 0 are left untouched
+ * -- the reference optimises val[mask] and writes it back, which is the same thing.  block0: first block of the
+ * tensor, blocks of 1024 elements; nblocks = total.  row > 0: mask index = element / row (channels-last grid,
+ * row = 32); row < 0: mask index = element % (-row) (NCDHW grid, -row = Z*Y*X).  lr: device double[groups] (the
+ * per-stage table, changed by the host between iterations); step: device int32[ntensors], steps taken so far per
+ * tensor -- the kernel applies step+1 and then increments the tensors that had a gradient, as torch.optim.Adam does.
+ * Graph-capturable: no host scalar changes between iterations. */
+int pn_adam_step(const void* table, int ntensors, int64_t nblocks, const double* lr, int32_t* step, double beta1, double beta2,
+                 double eps, void* stream);
+
+/* -------- ray pre-filter and pixel selection (src/Mapper.py:607-621, src/Tracker.py:206-226, 288-300) -------- */
+/* keep[r] = min_axis(max_pair((bound - o)/d)) >= gt_depth[r], float64 like the reference (bound: HOST double[6]). */
+int pn_ray_prefilter(const float* rays_o, const float* rays_d, const float* gt_depth, int64_t R, const double* bound,
+                     uint8_t* keep, void* stream);
+/* flags[y*Wc + x] = depth_img[H0+y][W0+x] > thresh over the crop (np.where(depth > 0.01) of Tracker.select_uv). */
+int pn_depth_pixel_flags(const float* depth_img, int W, int H0, int H1, int W0, int W1, float thresh, uint8_t* flags,
+                         void* stream);
+/* Stable compaction: ascending indices i with flags[i] != 0 -> idx_out[0..min(count,cap)), *count = their number
+ * (device int64).  scratch: device int32[(n + 1023)/1024]. */
+int pn_compact_flags(const uint8_t* flags, int64_t n, int32_t* scratch, int64_t* idx_out, int64_t cap, int64_t* count,
+                     void* stream);
+
+/* -------- keyframe overlap selection (src/Mapper.py:267-333) -------- */
+/* verts (R*n_samples,3) float32: points between 0.8*depth and depth+0.5 along each ray (Mapper.py:291-300);
+ * t_vals: device linspace(0,1,n_samples) float32. */
+int pn_overlap_points(const float* rays_o, const float* rays_d, const float* gt_depth, const float* t_vals, int64_t R,
+                      int n_samples, float* verts, void* stream);
+/* counts[k] = number of verts that project inside keyframe k's image (margin `edge`) in front of the camera
+ * (Mapper.py:302-320).  w2c: device (K,16) float32, the host's np.linalg.inv of every keyframe pose. */
+int pn_keyframe_overlap(const float* verts, int64_t n, const float* w2c, int K, double fx, double fy, double cx, double cy,
+                        int H, int W, int edge, int32_t* counts, void* stream);
+
+/* -------- dense-render consumers (src/utils/Mesher.py:53-212, src/utils/Visualizer.py:60-89) -------- */
+/* Mesher.point_masks over ONE chunk of points (keyframe branch): seen / forecast uint8 (n) (unseen = neither).
+ * w2c: device (K,16); depth_ptrs: DEVICE array of K device pointers to (H,W) depth images (depth_test != 0: bilinear
+ * grid_sample test against each keyframe's depth, forecast limited by max(depth_sample) over the chunk);
+ * kf_max: device float32 (K) = max(depth)*1.1 per keyframe (depth_test == 0).  scratch_max: K floats. */
+int pn_point_masks(const float* pts, int64_t n, const float* w2c, const float* const* depth_ptrs, const float* kf_max, int K,
+                   int H, int W, float fx, float fy, float cx, float cy, int depth_test, float* scratch_max, uint8_t* seen,
+                   uint8_t* forecast, void* stream);
+/* Visualizer panels: depth_res = |gt_depth - depth| (0 where gt_depth == 0), colour residual likewise, colours clipped
+ * to [0,1].  n pixels; depth float64 as render_img returns it. */
+int pn_vis_residuals(const float* gt_depth, const float* gt_color, const double* depth, const float* color, int64_t n,
+                     double* depth_res, float* gt_color_clip, float* color_clip, float* color_res, void* stream);
+
+/* -------- sparse gradient exchange of the data-parallel mapper (no reference counterpart: single GPU) --------
+ * A mapping iteration touches a few per cent of the voxel rows (32 floats = 128 bytes each) of a gradient grid.
+ * pn_sparse_rows_pack turns a dense [V][32] gradient into bitmap (V/32 words, bit r of word w = row 32w+r holds a
+ * non-zero), prefix (per word: packed position of its first set row) and the packed rows in ascending row order
+ * (at most `cap`; rows beyond it are counted in *overflow, which the caller must find 0).  *count = rows held.
+ * scratch: int32[(V + 1023)/1024]. */
+int pn_sparse_rows_pack(const float* dense, int64_t V, uint32_t* bitmap, uint32_t* prefix, float* rows, int64_t cap,
+                        int32_t* scratch, int64_t* count, int32_t* overflow, void* stream);
+/* dense[row] = sum over the nsrc sources, in source order, of that source's packed row, for every row some source
+ * holds (other rows are left as they are).  bitmaps / prefixes / rows: HOST arrays of nsrc device pointers (slices
+ * of an all-gathered buffer, or peer pointers into the other GPUs' symmetric buffers: the reads then travel over
+ * NVLink inside this kernel).  Same source order on every rank => bit-identical sums on every rank. */
+int pn_sparse_rows_apply(float* dense, int64_t V, int nsrc, const uint32_t* const* bitmaps, const uint32_t* const* prefixes,
+                         const float* const* rows, int64_t cap, void* stream);
+/* out[i] = src_0[i] + src_1[i] + ... in source order (decoder / pose gradients riding in the same exchange). */
+int pn_dense_sum(float* out, int64_t n, int nsrc, const float* const* srcs, void* stream);
 
 /* -------- utilities -------- */
 /* (1,32,Z,Y,X) contiguous <-> channels-last [Z][Y][X][32]; `to_channels_last` = 1 or 0. */

@@ -485,20 +485,24 @@ def regulation(scene: Scene, rays_d: Tensor, rays_o: Tensor, gt_depth: Tensor, s
 # --------------------------------------------------------------------------
 # caller losses (define the gradients fed to the backward)
 # --------------------------------------------------------------------------
-def tracking_loss(depth, var, color, gt_depth, gt_color, w_color=0.5, handle_dynamic=True):
-    """src/Tracker.py:306-330."""
+def tracking_loss(depth, var, color, gt_depth, gt_color, w_color=0.5, handle_dynamic=True, depth_supervision=True):
+    """src/Tracker.py:306-330 (depth_supervision=False: the fork's colour-only branch, :313-318)."""
     var = var.detach()
     if handle_dynamic:
         tmp = torch.abs(gt_depth - depth) / torch.sqrt(var + 1e-10)
         mask = (tmp < 10 * tmp.median()) & (gt_depth > 0)
     else:
         mask = gt_depth > 0
+    if not depth_supervision:
+        return torch.abs(gt_color - color)[mask].sum()
     loss = (torch.abs(gt_depth - depth) / torch.sqrt(var + 1e-10))[mask].sum()
     return loss + w_color * torch.abs(gt_color - color)[mask].sum()
 
 
-def mapping_loss(depth, color, gt_depth, gt_color, stage, w_color=0.2, nice=True):
-    """src/Mapper.py:628-646."""
+def mapping_loss(depth, color, gt_depth, gt_color, stage, w_color=0.2, nice=True, depth_supervision=True):
+    """src/Mapper.py:628-646 (depth_supervision=False: the fork's colour-only branch, :633-637)."""
+    if not depth_supervision:
+        return torch.abs(gt_color - color).sum()
     m = gt_depth > 0
     loss = torch.abs(gt_depth[m] - depth[m]).sum()
     if (not nice) or stage == "color":

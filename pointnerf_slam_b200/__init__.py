@@ -17,7 +17,7 @@ Modules
   csrc/     CUDA kernels (sm_100a) and the C ABI
 """
 
-from . import _lib, engine, common, decoder, config, renderer, graphs, losses  # noqa: E402,F401
+from . import _lib, engine, common, decoder, config, renderer, graphs, losses, mapper  # noqa: E402,F401
 from .renderer import Renderer  # noqa: E402,F401
 from .decoder import NICE, MLP, MLP_no_xyz  # noqa: E402,F401
 from .config import get_model, load_bound, grid_init, attach_bounds  # noqa: E402,F401

@@ -1,65 +1,22 @@
-// Fused decoder kernels for the NICE grid decoders (decoder.MLP, hidden 32).
+// C ABI of the NICE grid decoders (decoder.MLP, hidden 32) and the coarse-level decoder (decoder.MLP_no_xyz).
 //
-// One kernel evaluates, per sample: bound mask -> coordinate normalisation ->
-// trilinear gather from channels-last grids -> Fourier embedding -> 5 blocks
-// (relu(W h + b) + Wc c + bc, skip after block 2) -> output layer, replacing
-// the reference's ~60 ATen launches per decoder call
-// (src/conv_onet/models/decoder.py:168-203, src/common.py:269-284).
+// The grid decoders run on the tensor cores (pn_gridmlp_tc_fwd.cu, pn_gridmlp_tc_bwd.cu, pn_wgrad_tc.cu); this file
+// holds their entry points (argument checks, dispatch on c_dim / n_out / requested gradients) and the generic tiled
+// weight-gradient GEMM used when only some gradient sinks are requested.
 //
-// Work mapping.  A CTA of 256 threads owns a tile of 256 consecutive samples
-// (persistent over tiles).  Two phases alternate per tile:
-//   * feature phase, warp-cooperative: lane = channel.  For each of the warp's
-//     32 samples the 8 voxel corners are 8 fully coalesced 128-byte rows of the
-//     channels-last grid; the interpolated feature goes to a padded shared
-//     tile [channel][sample].  The backward walks the same pattern to scatter
-//     feature gradients (run-length aggregated over consecutive samples that
-//     share a voxel, then coalesced RED) and to form the coordinate gradient
-//     (warp-shuffle reduction over channels).
-//   * MLP phase, thread = sample: activations live in registers, weights are
-//     staged once per CTA in shared memory ([out][in] rows, 16-byte aligned)
-//     and read as warp-uniform LDS.128 broadcasts.
+// The coarse decoder (one 77 KB grid, 32-wide layers without embedding, its own Mapper process upstream) is a SIMT
+// kernel: a CTA of 256 threads owns 256 consecutive samples and alternates two phases per tile:
+//   * feature phase, warp-cooperative: lane = channel.  For each of the warp's 32 samples the 8 voxel corners are
+//     8 fully coalesced 128-byte rows of the channels-last grid; the interpolated feature goes to a padded shared
+//     tile [channel][sample].  The backward walks the same pattern to scatter feature gradients (run-length
+//     aggregated over consecutive samples that share a voxel, then coalesced RED) and to form the coordinate
+//     gradient (warp-shuffle reduction over channels).
+//   * MLP phase, thread = sample: activations live in registers, weights are staged once per CTA in shared memory
+//     ([out][in] rows, 16-byte aligned) and read as warp-uniform LDS.128 broadcasts.
 #include "pn_gridmlp.cuh"
 
 namespace pn {
 namespace {
-
-// ----------------------------- shared-memory weight layout (floats)
-constexpr int kEP = 96;                    // padded embedding width
-constexpr int OFF_B = 0;                   // [3][96]
-constexpr int OFF_W0 = OFF_B + 3 * kEP;    // [32][96]
-constexpr int OFF_W3E = OFF_W0 + 32 * kEP; // [32][96]  pts_linears.3.weight[:, :93]
-constexpr int OFF_WH = OFF_W3E + 32 * kEP; // [4][32][32]: W1, W2, W3[:,93:], W4
-constexpr int OFF_BIAS = OFF_WH + 4 * 1024;  // [5][32] pts biases
-constexpr int OFF_BC = OFF_BIAS + 160;     // [5][32] fc_c biases
-constexpr int OFF_WO = OFF_BC + 160;       // [4][32]
-constexpr int OFF_BO = OFF_WO + 128;       // [4]
-constexpr int OFF_WC = OFF_BO + 4;         // [5][32][CD]
-static_assert(OFF_WC % 4 == 0, "alignment");
-template <int CD> __host__ __device__ constexpr int wfloats() { return OFF_WC + 5 * 32 * CD; }
-template <int CD> __host__ __device__ constexpr size_t smem_bytes() { return (size_t)(wfloats<CD>() + CD * kLdc) * sizeof(float); }
-
-template <int CD, int NOUT>
-__device__ void stage_weights(const MlpDev& m, float* wsm) {
-  const int t = threadIdx.x, nt = blockDim.x;
-  for (int i = t; i < 3 * kEP; i += nt) { int d = i / kEP, k = i % kEP; wsm[OFF_B + i] = k < PN_EMBED ? m.B[d * PN_EMBED + k] : 0.f; }
-  for (int i = t; i < 32 * kEP; i += nt) {
-    int j = i / kEP, k = i % kEP;
-    wsm[OFF_W0 + i] = k < PN_EMBED ? m.W[0][j * PN_EMBED + k] : 0.f;
-    wsm[OFF_W3E + i] = k < PN_EMBED ? m.W[3][j * (PN_EMBED + 32) + k] : 0.f;
-  }
-  for (int i = t; i < 1024; i += nt) {
-    int j = i >> 5, k = i & 31;
-    wsm[OFF_WH + i] = m.W[1][i];
-    wsm[OFF_WH + 1024 + i] = m.W[2][i];
-    wsm[OFF_WH + 2048 + i] = m.W[3][j * (PN_EMBED + 32) + PN_EMBED + k];
-    wsm[OFF_WH + 3072 + i] = m.W[4][i];
-  }
-  for (int i = t; i < 160; i += nt) { wsm[OFF_BIAS + i] = m.b[i >> 5][i & 31]; wsm[OFF_BC + i] = m.bc[i >> 5][i & 31]; }
-  for (int i = t; i < 128; i += nt) wsm[OFF_WO + i] = i < NOUT * 32 ? m.Wo[i] : 0.f;
-  for (int i = t; i < 4; i += nt) wsm[OFF_BO + i] = i < NOUT ? m.bo[i] : 0.f;
-  for (int l = 0; l < 5; ++l)
-    for (int i = t; i < 32 * CD; i += nt) wsm[OFF_WC + l * 32 * CD + i] = m.Wc[l][i];
-}
 
 // acc[j] += sum_k W[j][k] x[k]   (W in shared memory, row stride LD)
 template <int K, int LD>
@@ -89,24 +46,6 @@ __device__ __forceinline__ void matvec_t(const float* __restrict__ W, const floa
       gx[4 * kc + 1] = fmaf(w.y, g[j], gx[4 * kc + 1]);
       gx[4 * kc + 2] = fmaf(w.z, g[j], gx[4 * kc + 2]);
       gx[4 * kc + 3] = fmaf(w.w, g[j], gx[4 * kc + 3]);
-    }
-  }
-}
-
-// acc[j] += sum_k Wc[j][k] c[k], c read from the shared feature tile column.
-template <int CD>
-__device__ __forceinline__ void feature_term(const float* __restrict__ Wc, const float* __restrict__ ccol, float (&acc)[32]) {
-#pragma unroll
-  for (int kc = 0; kc < CD / 4; ++kc) {
-    const float c0 = ccol[(4 * kc) * kLdc], c1 = ccol[(4 * kc + 1) * kLdc], c2 = ccol[(4 * kc + 2) * kLdc],
-                c3 = ccol[(4 * kc + 3) * kLdc];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float4 w = ld4(Wc + j * CD + 4 * kc);
-      acc[j] = fmaf(w.x, c0, acc[j]);
-      acc[j] = fmaf(w.y, c1, acc[j]);
-      acc[j] = fmaf(w.z, c2, acc[j]);
-      acc[j] = fmaf(w.w, c3, acc[j]);
     }
   }
 }
@@ -190,204 +129,6 @@ __device__ __forceinline__ void warp_scatter(const GridDev& g, float* __restrict
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if ((run_ok >> k) & 1u) atomicAdd(ggrid + run_base + corner_offset(k, g.W, g.H) + lane, run[k]);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------
-template <int CD, int NOUT>
-__global__ void __launch_bounds__(kThreads, CD == 32 ? 2 : 1) k_grid_mlp_fwd(const FwdArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* wsm = smem;
-  float* tile = smem + wfloats<CD>();
-  stage_weights<CD, NOUT>(a.w, wsm);
-  __syncthreads();
-  const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-  const int64_t N = a.pts.N, ntiles = (N + kThreads - 1) / kThreads;
-  const float* ccol = tile + tid;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t n = t * kThreads + tid;
-    const bool valid = n < N;
-    Sample sp;
-    sp.pf[0] = sp.pf[1] = sp.pf[2] = 0.f; sp.xn[0] = sp.xn[1] = sp.xn[2] = 0.f; sp.inside = true;
-    if (valid) load_sample(a.pts, n, a.nb, a.mb, sp);
-    const unsigned vm = __ballot_sync(kFull, valid);
-    __syncwarp();
-    warp_gather(a.ga, unnormalise(sp.xn[0], a.ga.W), unnormalise(sp.xn[1], a.ga.H), unnormalise(sp.xn[2], a.ga.D), vm,
-                lane, tile + lane * kLdc + wbase);
-    if (CD == 64)
-      warp_gather(a.gb, unnormalise(sp.xn[0], a.gb.W), unnormalise(sp.xn[1], a.gb.H), unnormalise(sp.xn[2], a.gb.D),
-                  vm, lane, tile + (32 + lane) * kLdc + wbase);
-    __syncwarp();
-    if (a.C && valid) {
-      float4* o = reinterpret_cast<float4*>(a.C);
-#pragma unroll
-      for (int q = 0; q < CD / 4; ++q)
-        o[(int64_t)q * N + n] = make_float4(ccol[(4 * q) * kLdc], ccol[(4 * q + 1) * kLdc], ccol[(4 * q + 2) * kLdc],
-                                            ccol[(4 * q + 3) * kLdc]);
-    }
-    // ---- Fourier embedding feeding block 0 and the skip part of block 3
-    float acc[32], acc3[32], h[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { acc[j] = wsm[OFF_BIAS + j]; acc3[j] = wsm[OFF_BIAS + 96 + j]; }
-#pragma unroll 1
-    for (int kc = 0; kc < kEP / 4; ++kc) {
-      const float4 b0 = ld4(wsm + OFF_B + 4 * kc), b1 = ld4(wsm + OFF_B + kEP + 4 * kc),
-                   b2 = ld4(wsm + OFF_B + 2 * kEP + 4 * kc);
-      float e[4];
-      e[0] = fourier_sin(fmaf(sp.pf[2], b2.x, fmaf(sp.pf[1], b1.x, sp.pf[0] * b0.x)));
-      e[1] = fourier_sin(fmaf(sp.pf[2], b2.y, fmaf(sp.pf[1], b1.y, sp.pf[0] * b0.y)));
-      e[2] = fourier_sin(fmaf(sp.pf[2], b2.z, fmaf(sp.pf[1], b1.z, sp.pf[0] * b0.z)));
-      e[3] = fourier_sin(fmaf(sp.pf[2], b2.w, fmaf(sp.pf[1], b1.w, sp.pf[0] * b0.w)));
-      if (a.E && valid) reinterpret_cast<float4*>(a.E)[(int64_t)kc * N + n] = make_float4(e[0], e[1], e[2], e[3]);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float4 w0 = ld4(wsm + OFF_W0 + j * kEP + 4 * kc);
-        acc[j] = fmaf(w0.x, e[0], acc[j]); acc[j] = fmaf(w0.y, e[1], acc[j]);
-        acc[j] = fmaf(w0.z, e[2], acc[j]); acc[j] = fmaf(w0.w, e[3], acc[j]);
-        const float4 w3 = ld4(wsm + OFF_W3E + j * kEP + 4 * kc);
-        acc3[j] = fmaf(w3.x, e[0], acc3[j]); acc3[j] = fmaf(w3.y, e[1], acc3[j]);
-        acc3[j] = fmaf(w3.z, e[2], acc3[j]); acc3[j] = fmaf(w3.w, e[3], acc3[j]);
-      }
-    }
-    // ---- blocks 0..4
-#pragma unroll 1
-    for (int l = 0; l < 5; ++l) {
-      if (l > 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = (l == 3) ? acc3[j] : wsm[OFF_BIAS + l * 32 + j];
-        matvec<32, 32>(wsm + OFF_WH + (l - 1) * 1024, h, acc);
-      }
-      uint32_t bits = 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        bits |= (acc[j] > 0.f) ? (1u << j) : 0u;
-        h[j] = fmaxf(acc[j], 0.f) + wsm[OFF_BC + l * 32 + j];
-      }
-      feature_term<CD>(wsm + OFF_WC + l * 32 * CD, ccol, h);
-      if (valid) {
-        if (a.relu_bits) a.relu_bits[(int64_t)l * N + n] = bits;
-        if (a.H) store_planar32(a.H + (int64_t)l * 32 * N, N, n, h);
-      }
-    }
-    // ---- output layer
-    float out[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int o = 0; o < NOUT; ++o) {
-      float s = wsm[OFF_BO + o];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) s = fmaf(wsm[OFF_WO + o * 32 + j], h[j], s);
-      out[o] = s;
-    }
-    if (valid) store_raw<NOUT>(a.raw, n, out, a.out_mode, a.apply_mask && !sp.inside);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// backward w.r.t. activations / features / points
-// ---------------------------------------------------------------------------
-template <int CD, int NOUT, bool GRID_GRAD, bool NEED_DP, bool WS>
-__global__ void __launch_bounds__(kThreads, 1) k_grid_mlp_bwd(const BwdArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* wsm = smem;
-  float* tile = smem + wfloats<CD>();  // only rows [0,32) are used here
-  stage_weights<CD, NOUT>(a.w, wsm);
-  __syncthreads();
-  const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-  const int64_t N = a.pts.N, ntiles = (N + kThreads - 1) / kThreads;
-  float* gcol = tile + tid;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t n = t * kThreads + tid;
-    const bool valid = n < N;
-    Sample sp;
-    sp.pf[0] = sp.pf[1] = sp.pf[2] = 0.f; sp.xn[0] = sp.xn[1] = sp.xn[2] = 0.f; sp.inside = true;
-    if (valid) load_sample(a.pts, n, a.nb, a.mb, sp);
-    const unsigned vm = __ballot_sync(kFull, valid);
-    float go[4] = {0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-      const float4 g = reinterpret_cast<const float4*>(a.g_raw)[n];
-      if (NOUT == 4) { go[0] = g.x; go[1] = g.y; go[2] = g.z; }  // 4th output is overwritten downstream
-      else go[0] = (a.apply_mask && !sp.inside) ? 0.f : g.w;
-    }
-    if (WS && valid) {
-      reinterpret_cast<float4*>(a.GO)[n] = make_float4(go[0], go[1], go[2], go[3]);
-      a.P32[n] = sp.pf[0]; a.P32[N + n] = sp.pf[1]; a.P32[2 * N + n] = sp.pf[2];
-    }
-    float gh[32], gx[32], gc[32], ga3[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o) s = fmaf(wsm[OFF_WO + o * 32 + j], go[o], s);
-      gh[j] = s; gc[j] = 0.f; ga3[j] = 0.f;
-    }
-#pragma unroll 1
-    for (int l = 4; l >= 0; --l) {
-      if (WS && valid) store_planar32(a.GH + (int64_t)l * 32 * N, N, n, gh);
-      if (GRID_GRAD || NEED_DP) matvec_t<32, CD>(wsm + OFF_WC + l * 32 * CD, gh, gc);  // own-grid half only
-      const uint32_t bits = valid ? a.relu_bits[(int64_t)l * N + n] : 0u;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) gh[j] = ((bits >> j) & 1u) ? gh[j] : 0.f;
-      if (WS && valid) store_planar32(a.GA + (int64_t)l * 32 * N, N, n, gh);
-      if (l == 3) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ga3[j] = gh[j];
-      }
-      if (l > 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) gx[j] = 0.f;
-        matvec_t<32, 32>(wsm + OFF_WH + (l - 1) * 1024, gh, gx);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) gh[j] = gx[j];
-      }
-    }
-    // gh now holds the gradient at block-0 pre-activations.
-    float gp[3] = {0.f, 0.f, 0.f};
-    if (NEED_DP || WS) {
-#pragma unroll 1
-      for (int kc = 0; kc < kEP / 4; ++kc) {
-        float ge[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 w0 = ld4(wsm + OFF_W0 + j * kEP + 4 * kc), w3 = ld4(wsm + OFF_W3E + j * kEP + 4 * kc);
-          ge[0] = fmaf(w0.x, gh[j], ge[0]); ge[0] = fmaf(w3.x, ga3[j], ge[0]);
-          ge[1] = fmaf(w0.y, gh[j], ge[1]); ge[1] = fmaf(w3.y, ga3[j], ge[1]);
-          ge[2] = fmaf(w0.z, gh[j], ge[2]); ge[2] = fmaf(w3.z, ga3[j], ge[2]);
-          ge[3] = fmaf(w0.w, gh[j], ge[3]); ge[3] = fmaf(w3.w, ga3[j], ge[3]);
-        }
-        const float4 b0 = ld4(wsm + OFF_B + 4 * kc), b1 = ld4(wsm + OFF_B + kEP + 4 * kc),
-                     b2 = ld4(wsm + OFF_B + 2 * kEP + 4 * kc);
-        const float bx[4] = {b0.x, b0.y, b0.z, b0.w}, by[4] = {b1.x, b1.y, b1.z, b1.w}, bz[4] = {b2.x, b2.y, b2.z, b2.w};
-        float gq[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float arg = fmaf(sp.pf[2], bz[q], fmaf(sp.pf[1], by[q], sp.pf[0] * bx[q]));
-          gq[q] = ge[q] * fourier_cos(arg);
-          gp[0] = fmaf(bx[q], gq[q], gp[0]); gp[1] = fmaf(by[q], gq[q], gp[1]); gp[2] = fmaf(bz[q], gq[q], gp[2]);
-        }
-        if (WS && valid) reinterpret_cast<float4*>(a.GARG)[(int64_t)kc * N + n] = make_float4(gq[0], gq[1], gq[2], gq[3]);
-      }
-    }
-    if (GRID_GRAD || NEED_DP) {
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) gcol[j * kLdc] = gc[j];
-      __syncwarp();
-      float dux, duy, duz;
-      const float ux = unnormalise(sp.xn[0], a.ga.W), uy = unnormalise(sp.xn[1], a.ga.H), uz = unnormalise(sp.xn[2], a.ga.D);
-      warp_scatter<GRID_GRAD, NEED_DP>(a.ga, a.g_grid, ux, uy, uz, vm, lane, tile + lane * kLdc + wbase, dux, duy, duz);
-      if (NEED_DP && valid) {
-        gp[0] += norm_grad(a.pts, a.nb, 0, dux);
-        gp[1] += norm_grad(a.pts, a.nb, 1, duy);
-        gp[2] += norm_grad(a.pts, a.nb, 2, duz);
-      }
-    }
-    if (NEED_DP && valid) {
-      float* o = a.g_pts + 3 * n;
-      if (a.accumulate_pts) { o[0] += gp[0]; o[1] += gp[1]; o[2] += gp[2]; }
-      else { o[0] = gp[0]; o[1] = gp[1]; o[2] = gp[2]; }
-    }
   }
 }
 
@@ -549,46 +290,6 @@ __global__ void __launch_bounds__(768) k_wgrad_B(const float* __restrict__ P32, 
       const int k = 4 * q + i;
       if (lane == 0 && k < PN_EMBED) atomicAdd(dB + d * PN_EMBED + k, v);
     }
-}
-
-template <int CD, int NOUT>
-int launch_fwd(const FwdArgs& a, cudaStream_t st) {
-  if (use_tensor_cores()) return launch_fwd_tc(CD, NOUT, a, st);
-  auto kern = k_grid_mlp_fwd<CD, NOUT>;
-  const size_t sm = smem_bytes<CD>();
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  const int64_t ntiles = (a.pts.N + kThreads - 1) / kThreads;
-  const int per_sm = CD == 32 ? 2 : 1;
-  const int grid = (int)((ntiles < (int64_t)sm_count() * per_sm) ? ntiles : (int64_t)sm_count() * per_sm);
-  kern<<<grid, kThreads, sm, st>>>(a);
-  return launch_status("k_grid_mlp_fwd");
-}
-
-template <int CD, int NOUT, bool GG, bool DP, bool WS>
-int launch_bwd_t(const BwdArgs& a, cudaStream_t st) {
-  if (use_tensor_cores()) return launch_bwd_tc(CD, NOUT, GG, DP, WS, a, st);
-  auto kern = k_grid_mlp_bwd<CD, NOUT, GG, DP, WS>;
-  const size_t sm = (size_t)(wfloats<CD>() + 32 * kLdc) * sizeof(float);
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  const int64_t ntiles = (a.pts.N + kThreads - 1) / kThreads;
-  const int grid = (int)((ntiles < (int64_t)sm_count()) ? ntiles : (int64_t)sm_count());
-  kern<<<grid, kThreads, sm, st>>>(a);
-  return launch_status("k_grid_mlp_bwd");
-}
-
-template <int CD, int NOUT>
-int launch_bwd(const BwdArgs& a, bool gg, bool dp, bool ws, cudaStream_t st) {
-  const int key = (gg ? 4 : 0) | (dp ? 2 : 0) | (ws ? 1 : 0);
-  switch (key) {
-    case 0: return launch_bwd_t<CD, NOUT, false, false, false>(a, st);
-    case 1: return launch_bwd_t<CD, NOUT, false, false, true>(a, st);
-    case 2: return launch_bwd_t<CD, NOUT, false, true, false>(a, st);
-    case 3: return launch_bwd_t<CD, NOUT, false, true, true>(a, st);
-    case 4: return launch_bwd_t<CD, NOUT, true, false, false>(a, st);
-    case 5: return launch_bwd_t<CD, NOUT, true, false, true>(a, st);
-    case 6: return launch_bwd_t<CD, NOUT, true, true, false>(a, st);
-    default: return launch_bwd_t<CD, NOUT, true, true, true>(a, st);
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -812,8 +513,7 @@ extern "C" int pn_grid_mlp_fwd(const pn_points* pts, const pn_grid_mlp* w, const
   a.relu_bits = stash ? stash->relu_bits : nullptr; a.H = stash ? stash->H : nullptr;
   a.C = stash ? stash->C : nullptr; a.E = stash ? stash->E : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  if (w->c_dim == 32) return w->n_out == 1 ? launch_fwd<32, 1>(a, st) : launch_fwd<32, 4>(a, st);
-  return w->n_out == 1 ? launch_fwd<64, 1>(a, st) : launch_fwd<64, 4>(a, st);
+  return launch_fwd_tc(w->c_dim, w->n_out, a, st);
 }
 
 extern "C" int pn_grid_mlp_bwd(const pn_points* pts, const pn_grid_mlp* w, const pn_grid* gridA, const pn_grid* gridB,
@@ -839,8 +539,7 @@ extern "C" int pn_grid_mlp_bwd(const pn_points* pts, const pn_grid_mlp* w, const
   a.P32 = ws ? ws->P32 : nullptr; a.GO = ws ? ws->GO : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   const bool gg = g_gridA != nullptr, dp = g_pts != nullptr, wsb = ws != nullptr;
-  if (w->c_dim == 32) return w->n_out == 1 ? launch_bwd<32, 1>(a, gg, dp, wsb, st) : launch_bwd<32, 4>(a, gg, dp, wsb, st);
-  return w->n_out == 1 ? launch_bwd<64, 1>(a, gg, dp, wsb, st) : launch_bwd<64, 4>(a, gg, dp, wsb, st);
+  return launch_bwd_tc(w->c_dim, w->n_out, gg, dp, wsb, a, st);
 }
 
 extern "C" int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash* stash, const pn_wscratch* ws,
@@ -852,7 +551,7 @@ extern "C" int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash
   }
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tensor_cores() && w->c_dim == 32) {   // one fused tensor-core kernel (GA = GH masked by the ReLU bits)
+  if (w->c_dim == 32) {   // one fused tensor-core kernel (GA = GH masked by the ReLU bits)
     if (!stash->relu_bits) {   // the tensor-core backward does not write GA for c_dim 32
       set_error("pn_grid_mlp_wgrad: stash->relu_bits is required");
       return 1;
@@ -885,7 +584,7 @@ extern "C" int pn_grid_mlp_wgrad(int64_t N, const pn_grid_mlp* w, const pn_stash
       add(GH, stash->C + c * blk, g->Wc[l] ? g->Wc[l] + 32 * c : nullptr, c == 0 ? g->bc[l] : nullptr, cd, 32);
   }
   a.nmats = nm;
-  if (nm > 0 && use_tensor_cores()) {  // all W / b / Wc / bc sinks present -> tensor-core GEMMs
+  if (nm > 0) {  // all W / b / Wc / bc sinks present -> tensor-core GEMMs
     const int rc = launch_wgrad_tc(N, cd, stash->H, stash->C, stash->E, ws->GA, ws->GH, g->W, g->b, g->Wc, g->bc, st);
     if (rc > 0) return 1;
     if (rc == 0) nm = 0;

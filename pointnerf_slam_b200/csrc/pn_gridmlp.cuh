@@ -49,12 +49,6 @@ struct BwdArgs {
 };
 
 
-inline bool use_tensor_cores() {
-  const char* e = getenv("PN_MLP_ENGINE");   // "ffma" forces the exact-FP32 FFMA kernels
-  return !(e && e[0] == 'f');
-}
-
-
 // tensor-core kernels (pn_gridmlp_tc_fwd.cu / pn_gridmlp_tc_bwd.cu): c_dim in {32, 64}, n_out in {1, 4}
 int launch_fwd_tc(int c_dim, int n_out, const FwdArgs& a, cudaStream_t st);
 int launch_bwd_tc(int c_dim, int n_out, bool grid_grad, bool need_dp, bool wstash, const BwdArgs& a, cudaStream_t st);

@@ -636,14 +636,16 @@ __global__ void __launch_bounds__(1024) k_max_f32(const float* __restrict__ x, i
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_mapping_loss(const double* __restrict__ depth, const float* __restrict__ color,
                                                        const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
-                                                       int64_t R, int use_color, float w_color, double* __restrict__ loss,
-                                                       double* __restrict__ g_depth, float* __restrict__ g_color) {
+                                                       int64_t R, int use_color, float w_color, int depth_sup,
+                                                       double* __restrict__ loss, double* __restrict__ g_depth,
+                                                       float* __restrict__ g_color) {
   __shared__ double red_d[32], red_c[32];
   double sd = 0.0, sc = 0.0;
+  if (!depth_sup) w_color = 1.0f;                  // Mapper.py:633-637: the colour term alone, unweighted
   for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {
     const float g = gt_depth[r];
     const double diff = (double)g - depth[r];      // float32 - float64 promotes to float64 (torch)
-    const bool m = g > 0.f;
+    const bool m = depth_sup && g > 0.f;
     if (m) sd += fabs(diff);
     // d|gt - depth| / d depth = -sign(gt - depth), sign(0) = 0
     g_depth[r] = m ? (diff > 0.0 ? -1.0 : (diff < 0.0 ? 1.0 : 0.0)) : 0.0;
@@ -678,38 +680,81 @@ __global__ void __launch_bounds__(1024) k_mapping_loss(const double* __restrict_
 // torch.median of n values is the element of rank (n-1)/2: tmp is sorted in shared memory (bitonic, padded with
 // +inf to a power of two), so R <= kTrackMaxRays.  Fixed summation order: deterministic.
 // ---------------------------------------------------------------------------
-constexpr int kTrackMaxRays = 8192;
+constexpr int kTrackMaxRays = 8192;   // up to here tmp is sorted in shared memory; beyond, the median comes from a radix select
+
+__device__ __forceinline__ double track_tmp(const double* depth, const double* var, const float* gt_depth, int r) {
+  return __ddiv_rn(fabs((double)gt_depth[r] - depth[r]), __dsqrt_rn(__dadd_rn(var[r], 1e-10)));
+}
 
 __global__ void __launch_bounds__(1024) k_tracking_loss(const double* __restrict__ depth, const double* __restrict__ var,
                                                         const float* __restrict__ color, const float* __restrict__ gt_depth,
                                                         const float* __restrict__ gt_color, int R, int handle_dynamic,
-                                                        int use_color, float w_color, double* __restrict__ loss,
+                                                        int use_color, float w_color, int depth_sup, double* __restrict__ loss,
                                                         double* __restrict__ g_depth, float* __restrict__ g_color) {
   extern __shared__ double srt[];
   __shared__ double red_d[32], red_c[32];
   __shared__ double thr_s;
+  __shared__ int hist[256];
+  __shared__ int nan_s;
+  __shared__ unsigned long long prefix_s;
+  __shared__ int rank_s;
   const int tid = threadIdx.x;
   double thr = 0.0;
+  if (!depth_sup) w_color = 1.0f;     // Tracker.py:313-318: the masked colour term alone, unweighted
   if (handle_dynamic) {
-    int P2 = 1;
-    while (P2 < R) P2 <<= 1;
-    for (int r = tid; r < P2; r += blockDim.x)
-      srt[r] = r < R ? __ddiv_rn(fabs((double)gt_depth[r] - depth[r]), __dsqrt_rn(__dadd_rn(var[r], 1e-10))) : __longlong_as_double(0x7ff0000000000000LL);
+    if (tid == 0) nan_s = 0;
     __syncthreads();
-    for (int k = 2; k <= P2; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < P2; i += blockDim.x) {
-          const int l = i ^ j;
-          if (l > i) {
-            const double a = srt[i], b = srt[l];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { srt[i] = b; srt[l] = a; }
+    const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+    if (R <= kTrackMaxRays) {
+      int P2 = 1;
+      while (P2 < R) P2 <<= 1;
+      for (int r = tid; r < P2; r += blockDim.x) {
+        const double t = r < R ? track_tmp(depth, var, gt_depth, r) : __longlong_as_double(0x7ff0000000000000LL);
+        if (t != t) nan_s = 1;          // torch.median propagates NaN: the mask becomes all-false
+        srt[r] = t;
+      }
+      __syncthreads();
+      for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < P2; i += blockDim.x) {
+            const int l = i ^ j;
+            if (l > i) {
+              const double a = srt[i], b = srt[l];
+              const bool up = (i & k) == 0;
+              if ((a > b) == up) { srt[i] = b; srt[l] = a; }
+            }
           }
+          __syncthreads();
+        }
+      }
+      if (tid == 0) thr_s = nan_s ? kNaN : __dmul_rn(10.0, srt[(R - 1) / 2]);
+    } else {
+      // radix select of the element of rank (R-1)/2: tmp >= 0, so the unsigned order of the bit patterns is the
+      // numeric order; eight 8-bit passes, most significant byte first, tmp recomputed on the fly
+      if (tid == 0) { prefix_s = 0ull; rank_s = (R - 1) / 2; }
+      __syncthreads();
+      for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = prefix_s;
+        const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        for (int r = tid; r < R; r += blockDim.x) {
+          const double t = track_tmp(depth, var, gt_depth, r);
+          if (t != t) { nan_s = 1; continue; }
+          const unsigned long long b = (unsigned long long)__double_as_longlong(t);
+          if ((b & hi_mask) == prefix) atomicAdd(&hist[(int)((b >> shift) & 0xffull)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int k = rank_s, bkt = 0;
+          while (bkt < 255 && k >= hist[bkt]) { k -= hist[bkt]; ++bkt; }
+          rank_s = k;
+          prefix_s = prefix | ((unsigned long long)bkt << shift);
         }
         __syncthreads();
       }
+      if (tid == 0) thr_s = nan_s ? kNaN : __dmul_rn(10.0, __longlong_as_double((long long)prefix_s));
     }
-    if (tid == 0) thr_s = __dmul_rn(10.0, srt[(R - 1) / 2]);
     __syncthreads();
     thr = thr_s;
   }
@@ -720,9 +765,9 @@ __global__ void __launch_bounds__(1024) k_tracking_loss(const double* __restrict
     const double inv = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(var[r], 1e-10)));
     const double t = __ddiv_rn(fabs(diff), __dsqrt_rn(__dadd_rn(var[r], 1e-10)));
     const bool m = (g > 0.f) && (!handle_dynamic || t < thr);
-    if (m) sd += t;
+    if (m && depth_sup) sd += t;
     // d(|gt - depth| / s)/d depth = -sign(gt - depth) / s
-    g_depth[r] = m ? (diff > 0.0 ? -inv : (diff < 0.0 ? inv : 0.0)) : 0.0;
+    g_depth[r] = (m && depth_sup) ? (diff > 0.0 ? -inv : (diff < 0.0 ? inv : 0.0)) : 0.0;
     if (use_color) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -898,28 +943,28 @@ extern "C" int pn_grid_transpose(const float* src, float* dst, int D, int H, int
 }
 
 extern "C" int pn_tracking_loss(const double* depth, const double* var, const float* color, const float* gt_depth,
-                                const float* gt_color, int64_t R, int handle_dynamic, int use_color, float w_color, double* loss,
-                                double* g_depth, float* g_color, void* stream) {
-  if (!depth || !var || !gt_depth || !loss || !g_depth || R < 1 || (use_color && (!color || !gt_color || !g_color))) {
+                                const float* gt_color, int64_t R, int handle_dynamic, int use_color, float w_color,
+                                int depth_supervision, double* loss, double* g_depth, float* g_color, void* stream) {
+  if (!depth || !var || !gt_depth || !loss || !g_depth || R < 1 || R > 0x7fffffff || (use_color && (!color || !gt_color || !g_color))) {
     set_error("pn_tracking_loss: bad arguments");
     return 1;
   }
-  if (R > pn::kTrackMaxRays) { set_error("pn_tracking_loss: at most %d rays", pn::kTrackMaxRays); return 1; }
   size_t sm = 0;
-  if (handle_dynamic) { size_t p2 = 1; while ((int64_t)p2 < R) p2 <<= 1; sm = p2 * sizeof(double); }
+  if (handle_dynamic && R <= pn::kTrackMaxRays) { size_t p2 = 1; while ((int64_t)p2 < R) p2 <<= 1; sm = p2 * sizeof(double); }
   cudaFuncSetAttribute(pn::k_tracking_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pn::kTrackMaxRays * sizeof(double)));
-  pn::k_tracking_loss<<<1, 1024, sm, PN_ST>>>(depth, var, color, gt_depth, gt_color, (int)R, handle_dynamic, use_color, w_color, loss,
-                                             g_depth, g_color);
+  pn::k_tracking_loss<<<1, 1024, sm, PN_ST>>>(depth, var, color, gt_depth, gt_color, (int)R, handle_dynamic, use_color, w_color,
+                                             depth_supervision, loss, g_depth, g_color);
   return launch_status("k_tracking_loss");
 }
 
 extern "C" int pn_mapping_loss(const double* depth, const float* color, const float* gt_depth, const float* gt_color, int64_t R,
-                               int use_color, float w_color, double* loss, double* g_depth, float* g_color, void* stream) {
+                               int use_color, float w_color, int depth_supervision, double* loss, double* g_depth, float* g_color,
+                               void* stream) {
   if (!depth || !gt_depth || !loss || !g_depth || R < 0 || (use_color && (!color || !gt_color || !g_color))) {
     set_error("pn_mapping_loss: bad arguments");
     return 1;
   }
-  k_mapping_loss<<<1, 1024, 0, PN_ST>>>(depth, color, gt_depth, gt_color, R, use_color, w_color, loss, g_depth, g_color);
+  k_mapping_loss<<<1, 1024, 0, PN_ST>>>(depth, color, gt_depth, gt_color, R, use_color, w_color, depth_supervision, loss, g_depth, g_color);
   return launch_status("k_mapping_loss");
 }
 

@@ -22,10 +22,11 @@ namespace umma {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- operand split -----------------------------------------------------------------------
+// Round to TF32 (10 mantissa bits), nearest with ties away from zero: bit-identical to cvt.rna.tf32.f32, but as one
+// integer add and one mask on the ALU pipe (the cvt is a multi-cycle conversion-pipe instruction: 5 % of the forward
+// kernel's stall samples in profiles/r2_*; a decoder pass converts 256 values per sample).
 __device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = tf32_hi(x);

@@ -393,8 +393,8 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                 f32 = dict(dtype=torch.float32, device=device)
                 ws = dict(GH=torch.empty(5 * 32 * n, **f32), GARG=torch.empty(96 * n, **f32),
                           P32=torch.empty(3 * n, **f32), GO=torch.empty(4 * n, **f32))
-                # GA is neither written nor read by the tensor-core engine for c_dim 32 (pnslam.h, pn_wscratch): alias it
-                tc32 = p.kind == "grid" and p.c_dim == 32 and _os.environ.get("PN_MLP_ENGINE", "")[:1] != "f"
+                # GA is neither written nor read for c_dim 32 (pnslam.h, pn_wscratch): alias it
+                tc32 = p.kind == "grid" and p.c_dim == 32
                 ws["GA"] = ws["GH"] if tc32 else torch.empty(5 * 32 * n, **f32)
                 wst = L.PnWscratch(*[ws[k].data_ptr() for k in ("GA", "GH", "GARG", "P32", "GO")])
             sst = stashes[i].struct()

@@ -38,16 +38,47 @@ class ImapStash:
         self.P32 = torch.empty(3 * n, **f32)
 
 
+NO_GRAD_CHUNK = 500000   # points per launch when no stash is kept (the reference's points_batch_size, Renderer.py:6-8)
+
+
+def _sub_points(pts, b: int, e: int) -> L.PnPoints:
+    """pn_points of the sample range [b, e) (ray mode: b and e are multiples of S)."""
+    s = L.PnPoints()
+    s.N = e - b
+    if pts.pts is not None:
+        base = pts.pts.data_ptr() + 3 * b * pts.pts.element_size()
+        if pts.pts.dtype == torch.float64:
+            s.pts64 = base
+        else:
+            s.pts32 = base
+        s.S = 1
+    else:
+        S = pts.z.shape[1]
+        r0 = b // S
+        s.rays_o, s.rays_d, s.z = pts.rays_o.data_ptr() + 12 * r0, pts.rays_d.data_ptr() + 12 * r0, pts.z.data_ptr() + 8 * b
+        s.S = S
+    return s
+
+
 def forward(p, pts, raw: torch.Tensor, mask_bound, device, save: bool, want_w: bool) -> Optional[ImapStash]:
+    """With `save` the whole batch is one launch and its activations (E 96 + H n_blocks x hidden + P32 3 floats per
+    sample) are the backward's stash.  Without it (torch.no_grad: render_img, meshing, the first pass of a two-pass
+    render) the batch is walked in chunks of NO_GRAD_CHUNK points through ONE chunk-sized activation buffer, so a
+    100k-ray render_img chunk or a 256^3 mesh query needs ~2 GB of scratch instead of 20-75 GB."""
     m = _struct(p)
     n = pts.n
-    st = ImapStash(n, m.hidden, m.n_blocks, device)
-    ps = pts.struct()
     mb = L.f64x6(mask_bound) if mask_bound is not None else None
-    with L.timed("imap_mlp_fwd", device):
-        L.check(L.lib().pn_imap_mlp_fwd(C.byref(ps), C.byref(m), mb, 1 if mb is not None else 0, C.c_void_p(raw.data_ptr()),
-                                        C.c_void_p(st.E.data_ptr()), C.c_void_p(st.H.data_ptr()), C.c_void_p(st.P32.data_ptr()),
-                                        C.c_void_p(L.stream_ptr(device))), "pn_imap_mlp_fwd")
+    S = 1 if pts.pts is not None else pts.z.shape[1]
+    step = n if save else max(S, NO_GRAD_CHUNK // S * S)
+    st = ImapStash(min(n, step), m.hidden, m.n_blocks, device)
+    for b in range(0, n, step):
+        e = min(n, b + step)
+        ps = pts.struct() if (b == 0 and e == n) else _sub_points(pts, b, e)
+        with L.timed("imap_mlp_fwd", device):
+            L.check(L.lib().pn_imap_mlp_fwd(C.byref(ps), C.byref(m), mb, 1 if mb is not None else 0,
+                                            C.c_void_p(raw.data_ptr() + 16 * b), C.c_void_p(st.E.data_ptr()),
+                                            C.c_void_p(st.H.data_ptr()), C.c_void_p(st.P32.data_ptr()),
+                                            C.c_void_p(L.stream_ptr(device))), "pn_imap_mlp_fwd")
     return st if save else None
 
 

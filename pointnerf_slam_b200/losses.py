@@ -16,7 +16,7 @@ from . import _lib as L
 
 class _MappingLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, depth, color, gt_depth, gt_color, w_color, use_color):
+    def forward(ctx, depth, color, gt_depth, gt_color, w_color, use_color, depth_supervision=True):
         dev = depth.device
         d = depth.detach().double().contiguous()
         gd = gt_depth.detach().float().contiguous()
@@ -31,7 +31,7 @@ class _MappingLossFn(torch.autograd.Function):
         with L.device_guard(dev):
             L.check(L.lib().pn_mapping_loss(C.c_void_p(d.data_ptr()), C.c_void_p(L.ptr(c)), C.c_void_p(gd.data_ptr()),
                                             C.c_void_p(L.ptr(gc)), C.c_int64(R), int(use_color), C.c_float(w_color),
-                                            C.c_void_p(loss.data_ptr()), C.c_void_p(g_depth.data_ptr()),
+                                            int(bool(depth_supervision)), C.c_void_p(loss.data_ptr()), C.c_void_p(g_depth.data_ptr()),
                                             C.c_void_p(L.ptr(g_color)), C.c_void_p(L.stream_ptr(dev))), "pn_mapping_loss")
         ctx.save_for_backward(g_depth, g_color)
         ctx.color_dtype = color.dtype if use_color else None
@@ -44,23 +44,27 @@ class _MappingLossFn(torch.autograd.Function):
         # a 0-dim multiplier does not promote the dtype of a dimensioned tensor: one launch each
         gd = (g_depth * go).to(ctx.depth_dtype) if ctx.needs_input_grad[0] else None
         gc = (g_color * go).to(ctx.color_dtype) if (g_color is not None and ctx.needs_input_grad[1]) else None
-        return gd, gc, None, None, None, None
+        return gd, gc, None, None, None, None, None
 
 
 def mapping_loss(depth: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
-                 gt_color: Optional[torch.Tensor], stage: str = "color", w_color: float = 0.2, nice: bool = True) -> torch.Tensor:
+                 gt_color: Optional[torch.Tensor], stage: str = "color", w_color: float = 0.2, nice: bool = True,
+                 depth_supervision: bool = True) -> torch.Tensor:
     """Mapper.py:628-646: masked L1 depth loss, plus ``w_color`` times the L1 colour loss in stage
-    ``color`` (always for iMAP*).  Returns a float64 scalar; differentiable w.r.t. depth and colour."""
+    ``color`` (always for iMAP*).  ``depth_supervision=False`` is the fork's colour-only branch (Mapper.py:633-637).
+    Returns a float64 scalar; differentiable w.r.t. depth and colour."""
     if not depth.is_cuda:
         raise RuntimeError("pointnerf_slam_b200.losses.mapping_loss needs CUDA tensors (there is no CPU path)")
     use_color = ((not nice) or stage == "color") and color is not None and gt_color is not None
+    if not depth_supervision and not use_color:
+        raise ValueError("mapping_loss: without depth supervision the loss is the colour term (stage 'color' or iMAP*)")
     return _MappingLossFn.apply(depth, color if use_color else None, gt_depth, gt_color if use_color else None,
-                                float(w_color), bool(use_color))
+                                float(w_color), bool(use_color), bool(depth_supervision))
 
 
 class _TrackingLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, depth, var, color, gt_depth, gt_color, w_color, use_color, handle_dynamic):
+    def forward(ctx, depth, var, color, gt_depth, gt_color, w_color, use_color, handle_dynamic, depth_supervision=True):
         dev = depth.device
         d = depth.detach().double().contiguous()
         v = var.detach().double().contiguous()
@@ -76,7 +80,7 @@ class _TrackingLossFn(torch.autograd.Function):
         with L.device_guard(dev):
             L.check(L.lib().pn_tracking_loss(C.c_void_p(d.data_ptr()), C.c_void_p(v.data_ptr()), C.c_void_p(L.ptr(c)),
                                              C.c_void_p(gd.data_ptr()), C.c_void_p(L.ptr(gc)), C.c_int64(R), int(handle_dynamic),
-                                             int(use_color), C.c_float(w_color), C.c_void_p(loss.data_ptr()),
+                                             int(use_color), C.c_float(w_color), int(bool(depth_supervision)), C.c_void_p(loss.data_ptr()),
                                              C.c_void_p(g_depth.data_ptr()), C.c_void_p(L.ptr(g_color)),
                                              C.c_void_p(L.stream_ptr(dev))), "pn_tracking_loss")
         ctx.save_for_backward(g_depth, g_color)
@@ -89,23 +93,25 @@ class _TrackingLossFn(torch.autograd.Function):
         g_depth, g_color = ctx.saved_tensors
         gd = (g_depth * go).to(ctx.depth_dtype) if ctx.needs_input_grad[0] else None
         gc = (g_color * go).to(ctx.color_dtype) if (g_color is not None and ctx.needs_input_grad[2]) else None
-        return gd, None, gc, None, None, None, None, None
+        return gd, None, gc, None, None, None, None, None, None
 
-
-TRACKING_LOSS_MAX_RAYS = 8192
 
 
 def tracking_loss(depth: torch.Tensor, uncertainty: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
                   gt_color: Optional[torch.Tensor], w_color: float = 0.5, use_color: bool = True,
-                  handle_dynamic: bool = True) -> torch.Tensor:
+                  handle_dynamic: bool = True, depth_supervision: bool = True) -> torch.Tensor:
     """Tracker.py:306-330: uncertainty-weighted masked L1 depth loss (the uncertainty is detached; with
     ``handle_dynamic`` rays whose weighted residual exceeds ten times the median are dropped) plus ``w_color`` times the
     masked L1 colour loss.  Value and gradient come from one launch (the reference spends ~28 elementwise, reduction
-    and sort launches on it, forward and backward).  Returns a float64 scalar."""
+    and sort launches on it, forward and backward).  ``depth_supervision=False`` is the fork's colour-only branch
+    (Tracker.py:313-318: the same mask, the masked colour residuals alone).  Any number of rays (the fork's tracker
+    passes every pixel with depth, Tracker.py:206-226).  Returns a float64 scalar."""
     if not depth.is_cuda:
         raise RuntimeError("pointnerf_slam_b200.losses.tracking_loss needs CUDA tensors (there is no CPU path)")
-    if depth.shape[0] > TRACKING_LOSS_MAX_RAYS or depth.shape[0] == 0:
-        raise ValueError(f"tracking_loss handles 1..{TRACKING_LOSS_MAX_RAYS} rays per call (got {depth.shape[0]})")
+    if depth.shape[0] == 0:
+        raise ValueError("tracking_loss needs at least one ray")
     use_color = bool(use_color) and color is not None and gt_color is not None
+    if not depth_supervision and not use_color:
+        raise ValueError("tracking_loss: without depth supervision the loss is the colour term (use_color_in_tracking)")
     return _TrackingLossFn.apply(depth, uncertainty, color if use_color else None, gt_depth, gt_color if use_color else None,
-                                 float(w_color), use_color, bool(handle_dynamic))
+                                 float(w_color), use_color, bool(handle_dynamic), bool(depth_supervision))

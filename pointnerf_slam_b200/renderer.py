@@ -202,8 +202,10 @@ class Renderer(object):
     # ------------------------------------------------------------------
     def eval_points(self, p, decoders, c=None, stage='color', device='cuda:0'):
         """Occupancy / colour of points, (N,3) -> (N,4); logit 100 outside the
-        bound (Renderer.py:23-61).  One fused pass per decoder; no chunking is
-        needed because no per-point activation is materialised in HBM."""
+        bound (Renderer.py:23-61).  One fused pass per decoder.  The NICE decoders keep activations on chip,
+        so no chunking is needed; the iMAP* MLP stages (N x 256) activations per layer, so without gradients
+        it walks the batch in chunks of 500k points through one scratch buffer (imap.forward), like the
+        reference's points_batch_size loop (Renderer.py:38-41)."""
         plan = self._plan(decoders, stage)
         if p.dim() != 2 or p.shape[1] != 3:
             raise RuntimeError(f"eval_points expects (N,3) points, got {tuple(p.shape)}")
@@ -244,6 +246,10 @@ class Renderer(object):
         cfg = _RayCfg(self.N_samples, self.N_surface, self.N_importance, bool(self.lindisp), float(self.perturb),
                       bool(self.occupancy), self.bound, bool(self.freeze_map), self._constants(dev))
         t_rand = None
+        if self.perturb > 0. and self.N_importance > 0:
+            # Renderer.py:188 draws random u for the importance samples when perturb > 0; this build resamples with the
+            # deterministic table only (every shipped config has perturb 0.0)
+            raise NotImplementedError("N_importance > 0 with perturb > 0 (random importance samples) is not built")
         if self.perturb > 0.:
             # the reference draws on the CPU generator and uploads (Renderer.py:170)
             t_rand = torch.rand((rays_o.shape[0], self.N_samples)).to(dev)
@@ -272,21 +278,54 @@ class Renderer(object):
 
     def regulation(self, c, decoders, rays_d, rays_o, gt_depth, device, stage='color', t_rand=None):
         """Densities of jittered samples between the camera and 0.85*depth
-        (iMAP* only, Renderer.py:263-301)."""
+        (iMAP* only, Renderer.py:263-301).  Differentiable w.r.t. the decoders and -- through
+        ``pts = o + d*z`` (Renderer.py:296-297) -- the rays, so that under bundle adjustment the
+        regulation loss reaches the camera tensors as it does in the reference (Mapper.py:650-655)."""
         dev = rays_o.device
         R = rays_o.shape[0]
         if t_rand is None:
             t_rand = torch.rand((R, self.N_samples))  # CPU generator, as the reference
         t_rand = t_rand.to(dev).float().contiguous()
-        ro = rays_o.detach().float().contiguous()
-        rd = rays_d.detach().float().contiguous()
         gt = gt_depth.detach().reshape(-1).float().contiguous()
-        pts = torch.empty((R * self.N_samples, 3), dtype=torch.float32, device=dev)
-        k = self._constants(dev)
-        with L.device_guard(dev):
-            L.check(L.lib().pn_regulation_points(C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(gt.data_ptr()),
-                                                 C.c_void_p(k["t_vals"].data_ptr()), C.c_void_p(t_rand.data_ptr()),
-                                                 C.c_int64(R), self.N_samples, C.c_void_p(pts.data_ptr()), None,
-                                                 C.c_void_p(L.stream_ptr(dev))), "pn_regulation_points")
+        pts = _RegulationPointsFn.apply(rays_o, rays_d, gt, t_rand, self._constants(dev)["t_vals"], self.N_samples)
         raw = self.eval_points(pts, decoders, c, stage, device)
         return raw[:, -1]
+
+
+class _RegulationPointsFn(torch.autograd.Function):
+    """(rays_o, rays_d) -> the float32 regulation sample points (R*S,3); backward sums the point gradients
+    back onto the rays (z depends on gt_depth and the jitter only, which carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, gt, t_rand, t_vals, n_samples):
+        dev = rays_o.device
+        ro = rays_o.detach().float().contiguous()
+        rd = rays_d.detach().float().contiguous()
+        R = ro.shape[0]
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        pts = torch.empty((R * n_samples, 3), dtype=torch.float32, device=dev)
+        z = torch.empty((R, n_samples), dtype=torch.float64, device=dev) if need else None
+        with L.device_guard(dev):
+            L.check(L.lib().pn_regulation_points(C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(gt.data_ptr()),
+                                                 C.c_void_p(t_vals.data_ptr()), C.c_void_p(t_rand.data_ptr()),
+                                                 C.c_int64(R), n_samples, C.c_void_p(pts.data_ptr()), C.c_void_p(L.ptr(z)),
+                                                 C.c_void_p(L.stream_ptr(dev))), "pn_regulation_points")
+        ctx.z = z
+        ctx.set_materialize_grads(False)
+        return pts
+
+    @staticmethod
+    def backward(ctx, g_pts):
+        if g_pts is None or ctx.z is None:
+            return None, None, None, None, None, None
+        z = ctx.z
+        R, S = z.shape
+        dev = z.device
+        g = g_pts.float().contiguous()
+        g_o = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        g_d = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        with L.device_guard(dev):
+            L.check(L.lib().pn_points_to_rays_bwd(C.c_void_p(g.data_ptr()), C.c_void_p(z.data_ptr()), C.c_int64(R), S,
+                                                  C.c_void_p(g_o.data_ptr()), C.c_void_p(g_d.data_ptr()),
+                                                  C.c_void_p(L.stream_ptr(dev))), "pn_points_to_rays_bwd")
+        return (g_o if ctx.needs_input_grad[0] else None, g_d if ctx.needs_input_grad[1] else None, None, None, None, None)

@@ -339,3 +339,99 @@ def test_tracking_loss_head_matches_oracle(handle_dynamic, R):
     torch.testing.assert_close(cc.grad.cpu(), color.grad, rtol=0, atol=0)
     if handle_dynamic:
         assert int((dd.grad == 0).sum()) > int((gt_depth == 0).sum()), "the median test must have dropped outliers"
+
+
+@pytest.mark.parametrize("R", [8192, 8193, 40000])
+def test_tracking_loss_any_number_of_rays(R):
+    """Beyond 8192 rays (the fork's tracker passes every pixel with depth, Tracker.py:206-226) the median comes from the
+    radix select: same mask and gradients as the oracle, including duplicate values around the median."""
+    import pointnerf_slam_b200 as P
+    g = torch.Generator().manual_seed(R)
+    depth = (1.0 + torch.rand(R, generator=g, dtype=torch.float64)).requires_grad_(True)
+    var = 1e-3 + 0.1 * torch.rand(R, generator=g, dtype=torch.float64)
+    color = torch.rand(R, 3, generator=g).requires_grad_(True)
+    gt_depth = (depth.detach() + 0.05 * torch.randn(R, generator=g, dtype=torch.float64)).float()
+    gt_depth[torch.rand(R, generator=g) < 0.1] = 0.0
+    gt_depth[torch.rand(R, generator=g) < 0.05] += 3.0
+    gt_depth[100:140] = gt_depth[100]                      # ties
+    with torch.no_grad():
+        depth[100:140] = depth[100]; var[100:140] = var[100]
+    gt_color = torch.rand(R, 3, generator=g)
+    ref = O.tracking_loss(depth, var, color, gt_depth, gt_color, 0.5, True)
+    ref.backward()
+    dd, cc = depth.detach().cuda().requires_grad_(True), color.detach().cuda().requires_grad_(True)
+    out = P.losses.tracking_loss(dd, var.cuda(), cc, gt_depth.cuda(), gt_color.cuda(), 0.5, True, True)
+    out.backward()
+    assert abs(out.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    torch.testing.assert_close(dd.grad.cpu(), depth.grad, rtol=1e-14, atol=0)
+    torch.testing.assert_close(cc.grad.cpu(), color.grad, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("R", [500, 9000])
+def test_tracking_loss_nan_residual_empties_the_mask(R):
+    """torch.median propagates NaN, so `tmp < 10*median` is false everywhere and the loss is 0 (Tracker.py:308-309)."""
+    import pointnerf_slam_b200 as P
+    g = torch.Generator().manual_seed(5)
+    depth = (1.0 + torch.rand(R, generator=g, dtype=torch.float64))
+    var = 1e-3 + 0.1 * torch.rand(R, generator=g, dtype=torch.float64)
+    var[R // 3] = float("nan")
+    color, gt_color = torch.rand(R, 3, generator=g), torch.rand(R, 3, generator=g)
+    gt_depth = 1.0 + torch.rand(R, generator=g)
+    ref = O.tracking_loss(depth, var, color, gt_depth, gt_color, 0.5, True)
+    dd = depth.cuda().requires_grad_(True)
+    out = P.losses.tracking_loss(dd, var.cuda(), color.cuda(), gt_depth.cuda(), gt_color.cuda(), 0.5, True, True)
+    out.backward()
+    assert ref.item() == 0.0 and out.item() == 0.0 and float(dd.grad.abs().sum()) == 0.0
+
+
+def test_loss_heads_without_depth_supervision():
+    """The fork's colour-only branches (Tracker.py:313-318, Mapper.py:633-637)."""
+    import pointnerf_slam_b200 as P
+    g = torch.Generator().manual_seed(8)
+    R = 1500
+    depth = (1.0 + torch.rand(R, generator=g, dtype=torch.float64)).requires_grad_(True)
+    var = 1e-3 + 0.1 * torch.rand(R, generator=g, dtype=torch.float64)
+    color = torch.rand(R, 3, generator=g).requires_grad_(True)
+    gt_depth = (depth.detach() + 0.05 * torch.randn(R, generator=g, dtype=torch.float64)).float()
+    gt_depth[torch.rand(R, generator=g) < 0.2] = 0.0
+    gt_color = torch.rand(R, 3, generator=g)
+    for name in ("tracking", "mapping"):
+        color.grad = None
+        if name == "tracking":
+            ref = O.tracking_loss(depth, var, color, gt_depth, gt_color, 0.5, True, depth_supervision=False)
+        else:
+            ref = O.mapping_loss(depth, color, gt_depth, gt_color, "color", 0.2, depth_supervision=False)
+        ref.backward()
+        dd, cc = depth.detach().cuda().requires_grad_(True), color.detach().cuda().requires_grad_(True)
+        if name == "tracking":
+            out = P.losses.tracking_loss(dd, var.cuda(), cc, gt_depth.cuda(), gt_color.cuda(), 0.5, True, True, depth_supervision=False)
+        else:
+            out = P.losses.mapping_loss(dd, cc, gt_depth.cuda(), gt_color.cuda(), "color", 0.2, depth_supervision=False)
+        out.backward()
+        assert abs(out.item() - ref.item()) <= 2e-6 * abs(ref.item()), name
+        torch.testing.assert_close(cc.grad.cpu(), color.grad, rtol=0, atol=0)
+        assert dd.grad is None or float(dd.grad.abs().sum()) == 0.0
+    assert depth.grad is None or float(depth.grad.abs().sum()) == 0.0
+
+
+def test_regulation_carries_the_pose_gradient():
+    """Renderer.regulation (Renderer.py:263-301) under bundle adjustment: the loss reaches the rays (and through them
+    the camera tensor) via pts = o + d*z (Renderer.py:296-297; used at Mapper.py:650-655).  iMAP* decoder with the
+    shipped checkpoint weights."""
+    from tests.test_gpu_imap import build
+    g = T.load("imap_render.npz")
+    model, r = build(g)
+    n = 64
+    ro, rd, gd = g["rays_o"][:n], g["rays_d"][:n], g["gt_depth"][:n]
+    t_rand = torch.rand(n, int(g["n_samples"]), generator=torch.Generator().manual_seed(3))
+    roc, rdc = ro.clone().requires_grad_(True), rd.clone().requires_grad_(True)
+    scene = O.Scene(T.state_dict(g), {}, g["bound"], nice=False, occupancy=False, n_samples=int(g["n_samples"]),
+                    n_surface=int(g["n_surface"]), n_importance=int(g["n_importance"]))
+    sig_ref = O.regulation(scene, rdc, roc, gd, "color", t_rand)
+    (0.0005 * sig_ref.abs().sum()).backward()
+    rog, rdg = ro.to(DEV).requires_grad_(True), rd.to(DEV).requires_grad_(True)
+    sig = r.regulation({}, model, rdg, rog, gd.to(DEV), DEV, "color", t_rand=t_rand)
+    (0.0005 * sig.abs().sum()).backward()
+    assert T.rel_max(sig, sig_ref) < 1e-4
+    assert rog.grad is not None and rdg.grad is not None
+    assert T.rel_max(rog.grad, roc.grad) < 2e-3 and T.rel_max(rdg.grad, rdc.grad) < 2e-3
