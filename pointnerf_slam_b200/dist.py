@@ -244,3 +244,190 @@ class OverlappedGradReducer:
                     leaf.grad.copy_(grad)
         self.items = []
         allreduce_gradients(list(late) + [t for t in others if t is not None])
+
+
+class SparseGradExchange:
+    """Gradient exchange of the data-parallel mapper that moves only what a mapping iteration touches.
+
+    A 5,000-ray batch leaves gradient in a few per cent of the voxel rows (one row = the 32 channels of a voxel = 128
+    bytes) of the middle / fine / colour grids, yet a dense all-reduce moves all 46 MiB of them.  Here every rank
+
+      1. packs its touched rows (``pn_sparse_rows_pack``: a bitmap of V/32 words, a per-word prefix, the rows in
+         ascending order) and its dense "tail" (decoder + pose gradients, ~60k floats) into ONE send buffer,
+      2. exchanges the buffers -- ``mode="allgather"``: one NCCL all-gather of fixed-size buffers;
+         ``mode="p2p"``: no collective at all, the buffers live in symmetric memory and step 3 reads the peers'
+         copies straight over NVLink (two device-side barriers fence the reads),
+      3. rebuilds the summed gradient in place (``pn_sparse_rows_apply`` / ``pn_dense_sum``): every touched row is the
+         sum of the ranks' rows IN RANK ORDER, so all ranks hold bit-identical gradients (what a replicated Adam step
+         needs) and the result does not depend on timing.
+
+    Row capacity per grid is fixed (``cap_frac`` of its rows) so that buffer sizes never depend on the data and the
+    whole exchange can sit inside a captured CUDA graph; a rank that touches more rows than that raises the device
+    counter ``overflow`` (checked by ``check_overflow()`` outside the graph; the caller then falls back to
+    ``allreduce_gradients``).  No reference counterpart: the reference is single-GPU.
+    """
+
+    def __init__(self, grid_shapes, tail_numel: int, device, cap_frac=0.25, mode: str = "allgather", group=None):
+        from . import _lib as L
+        self.L = L
+        self.device = torch.device(device)
+        self.world = world_size()
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.mode = mode
+        self.keys = list(grid_shapes)
+        self.V = {k: int(grid_shapes[k][0]) * int(grid_shapes[k][1]) * int(grid_shapes[k][2]) for k in self.keys}
+        frac = cap_frac if isinstance(cap_frac, dict) else {k: cap_frac for k in self.keys}
+        self.cap = {k: max(32, (int(self.V[k] * frac[k]) + 31) // 32 * 32) for k in self.keys}
+        self.tail_numel = int(tail_numel)
+        off, self.off = 0, {}
+        for k in self.keys:                       # float32 units; every section starts on a 128-byte boundary
+            nw = (self.V[k] + 31) // 32
+            nwp = (nw + 31) // 32 * 32
+            self.off[k] = (off, off + nwp, off + 2 * nwp)        # bitmap, prefix, rows
+            off += 2 * nwp + self.cap[k] * 32
+        self.off_tail = off
+        off += (self.tail_numel + 31) // 32 * 32
+        self.length = off
+        if mode == "p2p" and self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            group = group or dist.group.WORLD
+            self.group_name = group.group_name
+            self.send = symm.empty(self.length, dtype=torch.float32, device=self.device)
+            self.handle = symm.rendezvous(self.send, self.group_name)
+            self.send.zero_()
+            base = [int(self.handle.buffer_ptrs[r]) for r in range(self.world)]
+            self.recv = None
+        else:
+            self.mode = "allgather"
+            self.send = torch.zeros(self.length, dtype=torch.float32, device=self.device)
+            self.recv = torch.zeros(self.world * self.length, dtype=torch.float32, device=self.device)
+            base = [self.recv.data_ptr() + 4 * r * self.length for r in range(self.world)]
+        self.base = base
+        nscr = max((v + 1023) // 1024 for v in self.V.values()) + 1
+        self.scratch = torch.zeros(nscr, dtype=torch.int32, device=self.device)
+        self.count = torch.zeros(len(self.keys), dtype=torch.int64, device=self.device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        import ctypes as C
+        PtrArr = C.c_void_p * self.world
+        self._ptrs = {}
+        for k in self.keys:
+            ob, op, orow = self.off[k]
+            self._ptrs[k] = (PtrArr(*[b + 4 * ob for b in base]), PtrArr(*[b + 4 * op for b in base]), PtrArr(*[b + 4 * orow for b in base]))
+        self._tail_ptrs = PtrArr(*[b + 4 * self.off_tail for b in base])
+
+    def bytes_per_rank(self) -> int:
+        return 4 * self.length
+
+    def tail_view(self) -> torch.Tensor:
+        """The send buffer's dense tail: write the decoder / pose gradients here before ``exchange``."""
+        return self.send[self.off_tail:self.off_tail + self.tail_numel]
+
+    def exchange(self, grid_grads, tail_out=None) -> None:
+        """grid_grads: key -> dense channels-last gradient (any view of a [V][32] float32 block), summed in place
+        across ranks.  tail_out: flat float32 tensor of ``tail_numel`` elements that receives the summed tail."""
+        import ctypes as C
+        L, lib = self.L, self.L.lib()
+        st = C.c_void_p(L.stream_ptr(self.device))
+        with L.device_guard(self.device):
+            for i, k in enumerate(self.keys):
+                g = grid_grads[k]
+                ob, op, orow = self.off[k]
+                sp = self.send.data_ptr()
+                L.check(lib.pn_sparse_rows_pack(C.c_void_p(g.data_ptr()), C.c_int64(self.V[k]), C.c_void_p(sp + 4 * ob),
+                                                C.c_void_p(sp + 4 * op), C.c_void_p(sp + 4 * orow), C.c_int64(self.cap[k]),
+                                                C.c_void_p(self.scratch.data_ptr()), C.c_void_p(self.count[i:].data_ptr()),
+                                                C.c_void_p(self.overflow.data_ptr()), st), "pn_sparse_rows_pack")
+            if self.world > 1:
+                if self.mode == "p2p":
+                    self.handle.barrier(channel=0)                # every rank's buffer is complete
+                else:
+                    dist.all_gather_into_tensor(self.recv, self.send)
+            else:
+                self.recv.copy_(self.send)
+            for k in self.keys:
+                bm, pf, rows = self._ptrs[k]
+                L.check(lib.pn_sparse_rows_apply(C.c_void_p(grid_grads[k].data_ptr()), C.c_int64(self.V[k]), self.world, bm, pf, rows,
+                                                 C.c_int64(self.cap[k]), st), "pn_sparse_rows_apply")
+            if tail_out is not None and self.tail_numel:
+                L.check(lib.pn_dense_sum(C.c_void_p(tail_out.data_ptr()), C.c_int64(self.tail_numel), self.world, self._tail_ptrs, st),
+                        "pn_dense_sum")
+            if self.world > 1 and self.mode == "p2p":
+                self.handle.barrier(channel=1)                    # nobody overwrites a buffer a peer still reads
+
+    def check_overflow(self) -> None:
+        n = int(self.overflow.item())
+        if n:
+            self.overflow.zero_()
+            raise RuntimeError(f"SparseGradExchange: {n} touched voxel rows did not fit the send buffer "
+                               f"(capacities {self.cap}); raise cap_frac or fall back to allreduce_gradients")
+
+
+def gather_shards(x: torch.Tensor, total: int, world: Optional[int] = None) -> torch.Tensor:
+    """Concatenation over the ranks of their contiguous shards of a length-`total` leading dimension (shard r =
+    ``shard_bounds(total, r, world)``).  One all-gather of equal-size (padded) buffers; every rank gets the whole."""
+    world = world_size() if world is None else world
+    if world == 1:
+        return x
+    n_max = (total + world - 1) // world
+    buf = x.new_zeros((n_max,) + tuple(x.shape[1:]))
+    buf[:x.shape[0]].copy_(x)
+    out = x.new_empty((world * n_max,) + tuple(x.shape[1:]))
+    dist.all_gather_into_tensor(out, buf)
+    if total == world * n_max:
+        return out
+    parts = []
+    for r in range(world):
+        b, e = shard_bounds(total, r, world)
+        parts.append(out[r * n_max:r * n_max + (e - b)])
+    return torch.cat(parts, 0)
+
+
+def render_img_sharded(renderer, c, decoders, c2w, device, stage, gt_depth, rank: Optional[int] = None, world: Optional[int] = None):
+    """``Renderer.render_img`` (src/utils/Renderer.py:205-260) with the rays of every chunk sharded over the ranks and the
+    outputs all-gathered: every rank returns the full (H,W) depth, uncertainty and (H,W,3) colour.
+
+    The reference renders in chunks of ``ray_batch_size`` rays and clamps `far` with the maximum depth of the CHUNK
+    (Renderer.py:112 inside the loop of :237); each rank therefore takes its slice of every chunk and is told the
+    chunk's maximum (a local reduction: every rank holds the whole depth image), so the result equals the one-GPU
+    render ray for ray."""
+    from .common import get_rays
+    from .renderer import batch_depth_max
+    world = world_size() if world is None else world
+    rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
+    if world == 1:
+        return renderer.render_img(c, decoders, c2w, device, stage, gt_depth=gt_depth)
+    with torch.no_grad():
+        Hh, Ww = renderer.H, renderer.W
+        rays_o, rays_d = get_rays(Hh, Ww, renderer.fx, renderer.fy, renderer.cx, renderer.cy, c2w, device)
+        rays_o, rays_d, gd = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), gt_depth.reshape(-1)
+        n, bs = rays_d.shape[0], renderer.ray_batch_size
+        ds, us, cs = [], [], []
+        for i in range(0, n, bs):
+            m = min(bs, n - i)
+            b, e = shard_bounds(m, rank, world)
+            renderer.depth_max_override = batch_depth_max(gd[i:i + m].float().contiguous())
+            try:
+                d, u, col = renderer.render_batch_ray(c, decoders, rays_d[i + b:i + e], rays_o[i + b:i + e], device, stage,
+                                                      gt_depth=gd[i + b:i + e])
+            finally:
+                renderer.depth_max_override = None
+            ds.append(d.double()); us.append(u.double()); cs.append(col)
+        # one all-gather: [depth | uncertainty | colour] as float64 columns of this rank's rays (chunk-major)
+        mine = torch.cat([torch.cat(ds)[:, None], torch.cat(us)[:, None], torch.cat(cs).double()], 1)
+        per_rank = [sum(shard_bounds(min(bs, n - i), r, world)[1] - shard_bounds(min(bs, n - i), r, world)[0] for i in range(0, n, bs))
+                    for r in range(world)]
+        n_max = max(per_rank)
+        buf = mine.new_zeros((n_max, 5))
+        buf[:mine.shape[0]].copy_(mine)
+        out = mine.new_empty((world * n_max, 5))
+        dist.all_gather_into_tensor(out, buf)
+        # reassemble in ray order: chunk by chunk, rank by rank
+        pieces, off = [], [0] * world
+        for i in range(0, n, bs):
+            m = min(bs, n - i)
+            for r in range(world):
+                b, e = shard_bounds(m, r, world)
+                pieces.append(out[r * n_max + off[r]:r * n_max + off[r] + (e - b)])
+                off[r] += e - b
+        full = torch.cat(pieces, 0)
+        return full[:, 0].reshape(Hh, Ww), full[:, 1].reshape(Hh, Ww), full[:, 2:5].float().reshape(Hh, Ww, 3)

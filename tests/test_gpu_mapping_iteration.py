@@ -1,0 +1,115 @@
+"""The bench's mapping iteration -- exactly as bench.py builds and runs it (gradient arena, CUDA-graph replay, two-stream
+backward, fix_fine, colour decoder trained, bundle adjustment on 4 of 5 poses) -- against the oracle on the host cores
+at the FULL size: 5 x 1000 rays x 48 samples on the Replica-room0 grids.  Every gradient of the iteration is compared:
+three grids, every colour-decoder parameter (incl. the Fourier matrix B) and the four camera 7-vectors; then the same
+iteration with the optimiser step inside."""
+import pytest
+import torch
+
+import bench as B
+from tests import helpers as T
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def pair():
+    import pointnerf_slam_b200 as P
+    from pointnerf_slam_b200 import engine as E
+    w = B.build_mapping(DEV, 0, 1, B.PIX_PER_KF, "none", with_optimizer=False)
+    om = B.OracleMapping(B.PIX_PER_KF, with_optimizer=False)
+    # same decoders, grids, cameras, frames on both sides
+    sd = {k: v.detach().cpu() for k, v in w.model.state_dict().items()}
+    for k in om.sd:
+        om.sd[k] = sd[k].clone().requires_grad_(k.startswith("color_decoder."))
+    for k in om.c:
+        om.c[k] = w.grids[k].detach().cpu().contiguous().clone().requires_grad_(k != "grid_coarse")
+    om.cams = [c.detach().cpu().clone().requires_grad_(i > 0) for i, c in enumerate(w.cams)]
+    g = torch.Generator().manual_seed(99)
+    idx = [torch.randint(B.H * B.W, (B.PIX_PER_KF,), generator=g) for _ in range(B.N_KEYFRAMES)]
+    om.step(idx)
+    yield w, om, idx
+    E.GRAD_ARENA = None
+
+
+def _check_grads(w, om, tag):
+    msgs = []
+    for k in ("grid_middle", "grid_fine", "grid_color"):
+        msgs.append(T.assert_close_q(w.grids[k].grad, om.c[k].grad, rtol=1e-3, atol=0, rtol_max=0, atol_max=float(om.c[k].grad.abs().max()) * 5e-4,
+                                     q=0.999, what=f"{tag} grad {k}"))
+        assert float((om.c[k].grad.abs().sum(1) > 0).float().mean()) < 0.5
+    for name, p in w.model.named_parameters():
+        if not name.startswith("color_decoder."):
+            assert p.grad is None, name
+            continue
+        ref = om.sd[name].grad
+        assert T.rel_max(p.grad, ref) < 5e-4, (tag, name, T.rel_max(p.grad, ref))
+    for i in range(1, B.N_KEYFRAMES):
+        assert T.rel_max(w.cams[i].grad, om.cams[i].grad) < 5e-4, (tag, "camera", i)
+    assert w.cams[0].grad is None
+    return msgs
+
+
+def test_full_size_mapping_gradients_eager_two_stream(pair):
+    from pointnerf_slam_b200 import engine as E
+    w, om, idx = pair
+    assert E.PARALLEL_BACKWARD, "the bench default on one GPU"
+    w.iteration.zero_grad()
+    loss = w.iteration([i.to(DEV) for i in idx])
+    ref = float(om.last_loss) if hasattr(om, "last_loss") else None
+    print("\n".join(_check_grads(w, om, "eager")))
+    assert loss.dtype == torch.float64
+
+
+def test_full_size_mapping_gradients_graph_replay(pair):
+    """The captured iteration (what bench.py times): pixel indices are read from static tensors, so the replay sees the
+    oracle's draw; gradients after the replay are the oracle's."""
+    import pointnerf_slam_b200 as P
+    w, om, idx = pair
+    static_idx = [i.to(DEV).clone() for i in idx]
+    w.iteration.zero_grad()
+
+    def body():
+        for t in w.iteration.trained():
+            t.grad = None
+        return w.iteration(static_idx)
+    gs = P.graphs.GraphedStep(body, generators=[w.gen], warmup=2)
+    for t in static_idx:
+        t.zero_()                      # prove the replay reads the tensors, not captured values
+    gs()
+    torch.cuda.synchronize()
+    for t, i in zip(static_idx, idx):
+        t.copy_(i)
+    loss = gs()
+    torch.cuda.synchronize()
+    _check_grads(w, om, "graph")
+    assert gs.launches <= 40, gs.launches
+    gs.release()
+
+
+def test_mapping_iteration_with_optimizer_tracks_reference(pair):
+    """Three iterations with the frustum-masked Adam step inside (bench default): parameters follow the oracle's
+    torch.optim.Adam-on-val[mask] loop (Mapper.py:509-518, 657-674)."""
+    w2 = B.build_mapping(DEV, 0, 1, B.PIX_PER_KF, "none", with_optimizer=True)
+    om = B.OracleMapping(B.PIX_PER_KF, with_optimizer=True)
+    g = torch.Generator().manual_seed(7)
+    before = {k: w2.grids[k].detach().clone() for k in w2.masks}
+    for it in range(3):
+        idx = [torch.randint(B.H * B.W, (B.PIX_PER_KF,), generator=g) for _ in range(B.N_KEYFRAMES)]
+        om.step(idx)
+        w2.iteration([i.to(DEV) for i in idx])
+        w2.iteration.zero_grad()
+    for k, m in w2.masks.items():
+        a, b = w2.grids[k].detach().cpu(), om.c[k].detach()
+        assert T.rel_max(a, b) < 2e-3, k                         # Adam's sign-like first steps amplify tiny gradient differences
+        moved = (w2.grids[k].detach() != before[k]).any(1)[0]
+        assert bool((moved <= m.bool()).all()), f"{k}: a voxel outside the frustum mask moved"
+        assert int(moved.sum()) > 0
+    for name, p in w2.model.named_parameters():
+        if name.startswith("color_decoder."):
+            assert T.rel_max(p, om.sd[name]) < 2e-3, name
+    for i in range(1, B.N_KEYFRAMES):
+        assert T.rel_max(w2.cams[i], om.cams[i]) < 1e-3
+    from pointnerf_slam_b200 import engine as E
+    E.GRAD_ARENA = None
