@@ -632,21 +632,26 @@ class OracleMapping:
     :413-431 (val[mask] parameters of the frustum-selected voxels), :509-518 (write-back before the forward), :551-662
     (sampling, render, loss, backward, Adam step with the stage learning rates), :665-674 (write-back after the step)."""
 
-    def __init__(self, pix_per_kf, device="cpu", with_optimizer=True, seed=0):
+    def __init__(self, pix_per_kf, device="cpu", with_optimizer=True, seed=0, sd=None, grids=None, cams=None):
+        """sd / grids / cams: optional state to start from (CPU tensors: decoder state dict, (1,32,Z,Y,X) grids, camera
+        7-vectors) -- the parity tests hand over the CUDA arm's state; by default both arms are seeded independently."""
         from oracle import nice_oracle as O
         from oracle import mapper_oracle as M
         self.O, self.pix, self.dev = O, pix_per_kf, torch.device(device)
         self.bound = O.scene_bound(CFG["mapping"]["bound"], 1.0, 0.32)
         dev = self.dev
-        self.sd = {k: v.to(dev).requires_grad_(k.startswith("color_decoder.")) for k, v in O.init_nice_state(seed=seed).items()}
-        grids = O.init_grids(self.bound, CFG["grid_len"], 32, 2, True, torch.Generator().manual_seed(1))
+        sd = sd if sd is not None else O.init_nice_state(seed=seed)
+        self.sd = {k: v.detach().clone().to(dev).requires_grad_(k.startswith("color_decoder.")) for k, v in sd.items()}
+        if grids is None:
+            grids = O.init_grids(self.bound, CFG["grid_len"], 32, 2, True, torch.Generator().manual_seed(1))
         self.frames_host = synthetic_frames(N_KEYFRAMES, 100)
         self.frames = [(d.to(dev), c.to(dev)) for d, c in self.frames_host]
         poses = keyframe_poses(0)
         from pointnerf_slam_b200.common import get_tensor_from_camera      # host-side input preparation (Mapper.py:470)
-        self.cams = [get_tensor_from_camera(poses[k]).to(dev).requires_grad_(k > 0) for k in range(N_KEYFRAMES)]
+        cams = cams if cams is not None else [get_tensor_from_camera(poses[k]) for k in range(N_KEYFRAMES)]
+        self.cams = [c.detach().clone().to(dev).requires_grad_(k > 0) for k, c in enumerate(cams)]
         self.gen = torch.Generator(device=dev).manual_seed(5)
-        self.c = {k: v.to(dev) for k, v in grids.items()}
+        self.c = {k: v.detach().clone().contiguous().to(dev) for k, v in grids.items()}
         self.opt, self.masked = None, {}
         self.keys = ("grid_middle", "grid_fine", "grid_color")
         if with_optimizer:
