@@ -206,7 +206,8 @@ def build_scene(dev, nice=True):
     return P, bound, model, grids, P.Renderer(cfg, None, slam)
 
 
-def build_mapping(dev, rank, world, pix_per_kf=PIX_PER_KF, exchange="none", with_optimizer=True, arena=True, gen_seed=1234):
+def build_mapping(dev, rank, world, pix_per_kf=PIX_PER_KF, exchange="none", with_optimizer=True, arena=True, gen_seed=1234,
+                  shared_cameras=False):
     """The bench's mapping workload: scene, synthetic keyframes, camera tensors, MappingIteration (+ StageOptimizer over
     the frustum-selected voxels).  Also used by tests/test_gpu_mapping_iteration.py: ONE definition of the step."""
     P, bound, model, grids, renderer = build_scene(dev, True)
@@ -236,7 +237,7 @@ def build_mapping(dev, rank, world, pix_per_kf=PIX_PER_KF, exchange="none", with
                                 masks=masks, stage_lr=STAGE_LR, lr_factor=1.0, BA_cam_lr=0.001)
         opt.set_stage("color")
     it = MappingIteration(renderer, model, grids, frames, cams, H, W, FX, FY, CX, CY, pix_per_kf, "color", W_COLOR, generator=gen,
-                          arena=ar, exchange=exchange, optimizer=opt)
+                          arena=ar, exchange=exchange, optimizer=opt, shared_cameras=shared_cameras)
     return types.SimpleNamespace(P=P, bound=bound, model=model, grids=grids, renderer=renderer, frames=frames,
                                  frames_host=frames_host, poses=poses, cams=cams, gen=gen, arena=ar, optimizer=opt, masks=masks,
                                  iteration=it)
@@ -263,7 +264,9 @@ def run_ours(args):
         strong = args.scaling == "strong"
         pix = PIX_PER_KF // world if strong else PIX_PER_KF
         exchange = os.environ.get("PN_BENCH_EXCHANGE", "sparse") if world > 1 else "none"
-        w = build_mapping(dev, rank if not strong else 0, world, pix, exchange, with_optimizer=not args.no_optimizer)
+        # weak: every rank maps its own 5 keyframes (pose gradients stay local); strong: the rays of ONE 5-keyframe batch shard
+        w = build_mapping(dev, rank if not strong else 0, world, pix, exchange, with_optimizer=not args.no_optimizer,
+                          shared_cameras=strong)
         if strong:      # every rank holds the same keyframes; rank r draws its own pixels of them
             w.gen.manual_seed(1234 + rank)
         it = w.iteration
@@ -280,7 +283,8 @@ def run_ours(args):
                # gradient and the point (160+96+32+160+96+4+3 floats per sample) + 20 B of ReLU masks
                "grid_mlp_wgrad:color": n_samples * ((160 + 96 + 32 + 160 + 96 + 4 + 3) * 4 + 20)}
         info = {"workload": workload_name(args.scaling), "rays_per_step_per_gpu": units_rank, "samples_per_ray": S,
-                "grids": {k: list(v.shape) for k, v in w.grids.items()}, "parallelism": f"ray-shard dp{world}",
+                "grids": {k: list(v.shape) for k, v in w.grids.items()},
+                "parallelism": (f"ray-shard dp{world}" if strong else f"keyframe-shard dp{world}"),
                 "optimizer_in_step": not args.no_optimizer, "gradient_exchange": exchange,
                 "frustum_voxels": {k: int(m.sum()) for k, m in (w.masks or {}).items()}}
         if it._sparse is not None:

@@ -306,18 +306,21 @@ int pn_frustum_mask(const float* xs, int nx, const float* ys, int ny, const floa
                     const float* depth_img, float* scratch_depth, float* scratch_max, uint8_t* mask, void* stream);
 
 /* -------- optimiser step (src/Mapper.py:482-505, 529-536, 657-674; configs/nice_slam.yaml:71-95) --------
- * torch.optim.Adam (no weight decay, no amsgrad) over a table of tensors in ONE launch.  `table`: device array of
- * `ntensors` rows {float* p; const float* g; float* m; float* v; const uint8_t* mask; int64_t n; int32_t row;
- * int32_t group; int64_t block0} (64 bytes each; g == NULL: tensor skipped, as Adam skips parameters without
- * gradient).  mask (optional): one byte per `row` consecutive elements; elements whose byte is 0 are left untouched
- * -- the reference optimises val[mask] and writes it back, which is the same thing.  block0: first block of the
- * tensor, blocks of 1024 elements; nblocks = total.  row > 0: mask index = element / row (channels-last grid,
- * row = 32); row < 0: mask index = element % (-row) (NCDHW grid, -row = Z*Y*X).  lr: device double[groups] (the
- * per-stage table, changed by the host between iterations); step: device int32[ntensors], steps taken so far per
- * tensor -- the kernel applies step+1 and then increments the tensors that had a gradient, as torch.optim.Adam does.
+ * torch.optim.Adam (no weight decay, no amsgrad) over a table of tensors in ONE launch (+ a one-block kernel that
+ * advances the step counts and forms the bias corrections).  `table`: device array of `ntensors` rows
+ * {float* p; const float* g; float* m; float* v; const int64_t* idx; int64_t n; int64_t nwork; int32_t row;
+ * int32_t group; int64_t block0} (72 bytes each; g == NULL: tensor skipped, as Adam skips parameters without
+ * gradient).  idx (optional): ascending indices of the selected voxels -- the frustum mask compacted once per
+ * mapping call; only those voxels are visited and only they carry Adam state, exactly like the reference, which
+ * optimises val[mask] and writes it back (Mapper.py:413-431, 511-518, 665-674).  nwork = elements to update
+ * (n, or selected voxels x channels); row > 0: channels-last grid (element = voxel * row + channel, row = 32);
+ * row < 0: NCDHW grid (element = channel * (-row) + voxel, -row = Z*Y*X).  block0: first block of the tensor,
+ * blocks of 1024 work elements; nblocks = total.  lr: device double[groups] (the per-stage table, changed by the
+ * host between iterations); step: device int32[ntensors], steps taken so far per tensor (advanced for the tensors
+ * that have a gradient, as torch.optim.Adam does); hyper: device scratch, 2 floats per tensor.
  * Graph-capturable: no host scalar changes between iterations. */
-int pn_adam_step(const void* table, int ntensors, int64_t nblocks, const double* lr, int32_t* step, double beta1, double beta2,
-                 double eps, void* stream);
+int pn_adam_step(const void* table, int ntensors, int64_t nblocks, const double* lr, int32_t* step, float* hyper, double beta1,
+                 double beta2, double eps, void* stream);
 
 /* -------- ray pre-filter and pixel selection (src/Mapper.py:607-621, src/Tracker.py:206-226, 288-300) -------- */
 /* keep[r] = min_axis(max_pair((bound - o)/d)) >= gt_depth[r], float64 like the reference (bound: HOST double[6]). */

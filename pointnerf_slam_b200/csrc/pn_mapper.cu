@@ -153,28 +153,40 @@ __global__ void __launch_bounds__(256) k_frustum_mask(const FrustumArgs a) {
 // ---------------------------------------------------------------------------------------------
 // masked multi-tensor Adam (torch.optim.Adam, single-tensor arithmetic; src/Mapper.py:482-505, 657-674)
 // ---------------------------------------------------------------------------------------------
-struct AdamTensor {      // one row of the device descriptor table (8 x 8 bytes)
+struct AdamTensor {      // one row of the device descriptor table (9 x 8 bytes)
   float* p; const float* g; float* m; float* v;
-  const uint8_t* mask;   // one byte per `row` consecutive elements, or NULL
-  int64_t n;             // elements
-  int32_t row;           // > 0: elements per mask byte (32 for a channels-last grid); < 0: mask index = element % (-row)
+  const int64_t* idx;    // ascending indices of the selected voxels (the frustum mask, compacted once), or NULL = every element
+  int64_t n;             // elements of the tensor
+  int64_t nwork;         // elements to update: n, or (selected voxels) x (channels)
+  int32_t row;           // > 0: channels-last grid, element = voxel * row + channel; < 0: NCDHW grid, element = channel * (-row) + voxel
   int32_t group;
   int64_t block0;        // first block of this tensor in the launch
 };
 
 struct AdamGroups {
   const double* lr;      // device, per group (changed by the host between replays of a captured step)
-  const int32_t* step;   // device, per TENSOR: steps taken so far (the kernel applies step + 1)
+  int32_t* step;         // device, per TENSOR: steps taken so far
+  float2* hyper;         // device, per TENSOR: (lr / (1 - beta1^step), sqrt(1 - beta2^step)) of the step being taken
   double beta1, beta2, eps;
   int ntensors;
 };
 
 constexpr int kAdamPerBlock = 256 * 4;
 
+// torch.optim.Adam keeps one step count per parameter and advances it only when the parameter has a gradient
+__global__ void k_adam_prepare(const AdamTensor* __restrict__ tab, const AdamGroups g) {
+  for (int i = threadIdx.x; i < g.ntensors; i += blockDim.x) {
+    if (tab[i].g == nullptr) continue;
+    const int step = g.step[i] + 1;
+    g.step[i] = step;
+    const double bc1 = 1.0 - pow(g.beta1, (double)step), bc2 = 1.0 - pow(g.beta2, (double)step);
+    g.hyper[i] = make_float2((float)(g.lr[tab[i].group] / bc1), (float)sqrt(bc2));
+  }
+}
+
 __global__ void __launch_bounds__(256) k_adam(const AdamTensor* __restrict__ tab, const AdamGroups g) {
   __shared__ AdamTensor t;
-  __shared__ float s_step_size, s_bc2_sqrt;
-  __shared__ int s_skip;
+  __shared__ float2 hyper_s;
   if (threadIdx.x == 0) {
     int lo = 0, hi = g.ntensors - 1;           // last tensor whose block0 <= blockIdx.x
     while (lo < hi) {
@@ -182,22 +194,23 @@ __global__ void __launch_bounds__(256) k_adam(const AdamTensor* __restrict__ tab
       if (tab[mid].block0 <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
     }
     t = tab[lo];
-    const int step = g.step[lo] + 1;
-    const double bc1 = 1.0 - pow(g.beta1, (double)step), bc2 = 1.0 - pow(g.beta2, (double)step);
-    s_step_size = (float)(g.lr[t.group] / bc1);
-    s_bc2_sqrt = (float)sqrt(bc2);
-    s_skip = t.g == nullptr;
+    hyper_s = g.hyper[lo];
   }
   __syncthreads();
-  if (s_skip) return;
-  const float b2 = (float)g.beta2, eps = (float)g.eps, step_size = s_step_size, bc2s = s_bc2_sqrt;
+  if (t.g == nullptr) return;
+  const float b2 = (float)g.beta2, eps = (float)g.eps, step_size = hyper_s.x, bc2s = hyper_s.y;
   const float omb1 = (float)(1.0 - g.beta1), omb2 = (float)(1.0 - g.beta2);
   const int64_t base = ((int64_t)blockIdx.x - t.block0) * kAdamPerBlock;
+  const int64_t chans = t.row > 0 ? (int64_t)t.row : (t.row < 0 ? t.n / (int64_t)(-t.row) : 1);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t i = base + (int64_t)k * 256 + threadIdx.x;
-    if (i >= t.n) break;
-    if (t.mask && !t.mask[t.row > 0 ? i / t.row : i % (int64_t)(-t.row)]) continue;
+    const int64_t e = base + (int64_t)k * 256 + threadIdx.x;
+    if (e >= t.nwork) break;
+    int64_t i = e;
+    if (t.idx) {
+      const int64_t vox = t.idx[e / chans], ch = e % chans;
+      i = t.row > 0 ? vox * chans + ch : ch * (int64_t)(-t.row) + vox;
+    }
     const float gr = t.g[i];
     float m = t.m[i], v = t.v[i];
     m = __fadd_rn(m, __fmul_rn(omb1, __fsub_rn(gr, m)));                       // exp_avg.lerp_(grad, 1 - beta1)
@@ -206,12 +219,6 @@ __global__ void __launch_bounds__(256) k_adam(const AdamTensor* __restrict__ tab
     t.p[i] = __fadd_rn(t.p[i], __fmul_rn(-step_size, __fdiv_rn(m, denom)));    // addcdiv_(exp_avg, denom, -step_size)
     t.m[i] = m; t.v[i] = v;
   }
-}
-
-// torch.optim.Adam keeps one step count per parameter and advances it only when the parameter has a gradient
-__global__ void k_adam_advance(const AdamTensor* __restrict__ tab, int32_t* step, int ntensors) {
-  for (int i = threadIdx.x; i < ntensors; i += blockDim.x)
-    if (tab[i].g != nullptr) step[i] += 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -612,19 +619,19 @@ extern "C" int pn_frustum_mask(const float* xs, int nx, const float* ys, int ny,
   return launch_status("k_frustum_mask");
 }
 
-extern "C" int pn_adam_step(const void* table, int ntensors, int64_t nblocks, const double* lr, int32_t* step, double beta1,
-                            double beta2, double eps, void* stream) {
-  if (!table || !lr || !step || ntensors <= 0 || nblocks <= 0 || nblocks > 0x7fffffff) {
+extern "C" int pn_adam_step(const void* table, int ntensors, int64_t nblocks, const double* lr, int32_t* step, float* hyper,
+                            double beta1, double beta2, double eps, void* stream) {
+  if (!table || !lr || !step || !hyper || ntensors <= 0 || nblocks <= 0 || nblocks > 0x7fffffff) {
     set_error("pn_adam_step: bad arguments (ntensors %d, nblocks %lld)", ntensors, (long long)nblocks);
     return 1;
   }
   AdamGroups g;
-  g.lr = lr; g.step = step; g.beta1 = beta1; g.beta2 = beta2; g.eps = eps; g.ntensors = ntensors;
+  g.lr = lr; g.step = step; g.hyper = reinterpret_cast<float2*>(hyper); g.beta1 = beta1; g.beta2 = beta2; g.eps = eps; g.ntensors = ntensors;
   cudaStream_t st = (cudaStream_t)stream;
+  k_adam_prepare<<<1, 128, 0, st>>>(reinterpret_cast<const AdamTensor*>(table), g);
+  if (launch_status("k_adam_prepare")) return 1;
   k_adam<<<(unsigned)nblocks, 256, 0, st>>>(reinterpret_cast<const AdamTensor*>(table), g);
-  if (launch_status("k_adam")) return 1;
-  k_adam_advance<<<1, 128, 0, st>>>(reinterpret_cast<const AdamTensor*>(table), step, ntensors);
-  return launch_status("k_adam_advance");
+  return launch_status("k_adam");
 }
 
 // shared by the three compaction entry points: flags -> idx_out[0..count), *count.  scratch: int32[(n+1023)/1024 + 1]

@@ -105,7 +105,7 @@ class StageOptimizer:
         self.stage_lr = stage_lr
         self.lr_factor, self.BA_cam_lr = float(lr_factor), float(BA_cam_lr)
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
-        self.entries = []   # (param, mask or None, row, group)
+        self.entries = []   # (param, selected voxel indices or None, row, group)
         dev = None
         for key, g in grids.items():
             _cuda(g, key, torch.float32)
@@ -123,7 +123,7 @@ class StageOptimizer:
                 m = m.to(torch.uint8) if m.dtype != torch.uint8 else m
                 if m.numel() != zyx:
                     raise RuntimeError(f"{key}: the mask must have Z*Y*X = {zyx} elements, got {m.numel()}")
-                m = m.contiguous()
+                m = _compact(m.contiguous())          # ascending voxel indices: the step visits the selected voxels only
             self.entries.append((g, m, row, GRID_GROUP[key]))
         for p in decoder_params:
             _cuda(p, "decoder parameter", torch.float32)
@@ -143,6 +143,7 @@ class StageOptimizer:
         self.exp_avg_sq = [torch.zeros_like(p) for p, *_ in self.entries]
         self.lr = torch.zeros(self.NGROUPS, dtype=torch.float64, device=dev)
         self.step_count = torch.zeros(len(self.entries), dtype=torch.int32, device=dev)   # per tensor, as torch.optim.Adam
+        self._hyper = torch.zeros(2 * len(self.entries), dtype=torch.float32, device=dev)
         self._table = None
         self._table_key = None
         self._nblocks = 0
@@ -178,19 +179,21 @@ class StageOptimizer:
                     raise RuntimeError("StageOptimizer: a gradient must be float32 with its parameter's memory layout")
                 gp = g.data_ptr()
             n = p.numel()
-            rows.append(struct.pack("<5Q q i i q", p.data_ptr(), gp, ea.data_ptr(), es.data_ptr(), 0 if m is None else m.data_ptr(),
-                                    n, row, group, block0))
-            block0 += (n + 1023) // 1024
+            chans = row if row > 0 else (n // -row if row < 0 else 1)
+            nwork = n if m is None else m.numel() * chans
+            rows.append(struct.pack("<5Q q q i i q", p.data_ptr(), gp, ea.data_ptr(), es.data_ptr(), 0 if m is None else m.data_ptr(),
+                                    n, nwork, row if m is not None else 1, group, block0))
+            block0 += max(1, (nwork + 1023) // 1024)
         raw = np.frombuffer(b"".join(rows), dtype=np.uint8).copy()
         self._table = torch.from_numpy(raw).to(self.device)
         self._table_key, self._nblocks = key, block0
 
     def step(self) -> None:
         self._build_table()
-        with L.device_guard(self.device):
+        with L.device_guard(self.device), L.timed("adam_step", self.device):
             L.check(L.lib().pn_adam_step(C.c_void_p(self._table.data_ptr()), len(self.entries), C.c_int64(self._nblocks),
                                          C.c_void_p(self.lr.data_ptr()), C.c_void_p(self.step_count.data_ptr()),
-                                         self.betas[0], self.betas[1], self.eps,
+                                         C.c_void_p(self._hyper.data_ptr()), self.betas[0], self.betas[1], self.eps,
                                          C.c_void_p(L.stream_ptr(self.device))), "pn_adam_step")
 
     def zero_grad(self, set_to_none: bool = True) -> None:

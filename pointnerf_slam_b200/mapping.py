@@ -32,10 +32,12 @@ class MappingIteration:
     def __init__(self, renderer, decoders, grids: Dict[str, torch.Tensor], frames: Sequence, cams: Sequence[torch.Tensor],
                  H, W, fx, fy, cx, cy, pix_per_frame: int, stage: str = "color", w_color: float = 0.2,
                  generator: Optional[torch.Generator] = None, arena: Optional[E.GradArena] = None,
-                 exchange: str = "none", optimizer=None, trained_decoders: Sequence[str] = ("color",)):
+                 exchange: str = "none", optimizer=None, trained_decoders: Sequence[str] = ("color",), shared_cameras: bool = True):
         """frames: [(depth (H,W) f32, colour (H,W,3))] device tensors, one per keyframe; cams: camera 7-vectors (those
         with requires_grad are bundle-adjusted).  exchange: 'none' | 'sparse' | 'sparse_p2p' | 'dense' | 'overlap' |
-        'arena' -- how the gradients of a ray-sharded batch are summed over the ranks (dist.py)."""
+        'arena' -- how the gradients of a sharded batch are summed over the ranks (dist.py).  shared_cameras: True when
+        every rank holds the same keyframes and the RAYS are sharded (pose gradients are summed too); False when the
+        KEYFRAMES are sharded (each camera's gradient stays on the rank that owns the keyframe)."""
         self.renderer, self.decoders, self.grids, self.frames, self.cams = renderer, decoders, grids, list(frames), list(cams)
         self.geom = (int(H), int(W), float(fx), float(fy), float(cx), float(cy))
         self.n, self.stage, self.w_color, self.gen = int(pix_per_frame), stage, float(w_color), generator
@@ -46,10 +48,11 @@ class MappingIteration:
                             if any(p.requires_grad for p in getattr(decoders, name + "_decoder").parameters())}
         self.dec_params = [p for m in self.dec_modules.values() for p in m.parameters() if p.requires_grad]
         self.ba_cams = [c for c in self.cams if c.requires_grad]
+        self.shared_cams = [c for c in self.ba_cams] if shared_cameras else []
         self.world = D.world_size()
         self._sparse = None
         self._reducer = None
-        self._tail_items = self.dec_params + self.ba_cams
+        self._tail_items = self.dec_params + self.shared_cams
         self._tail_off, tail = [], 0
         for p in self._tail_items:                       # 16-byte aligned slots of the exchange's dense tail
             self._tail_off.append(tail)
@@ -114,13 +117,13 @@ class MappingIteration:
                 with self._reducer:
                     loss.backward()
                 self._reducer.finish({k: self.grids[k] for k in self.grid_keys}, decoders=dict(self.dec_modules),
-                                     others=[c.grad for c in self.ba_cams])
+                                     others=[c.grad for c in self.shared_cams])
             else:
                 loss.backward()
                 if self._sparse is not None:
                     self._exchange_sparse()
                 elif self.world > 1 and self.exchange == "dense":
-                    D.allreduce_gradients([t.grad for t in self.trained()])
+                    D.allreduce_gradients([self.grids[k].grad for k in self.grid_keys] + [p.grad for p in self._tail_items])
         finally:
             if self.arena is not None:
                 E.GRAD_ARENA = None
