@@ -237,7 +237,7 @@ def build_mapping(dev, rank, world, pix_per_kf=PIX_PER_KF, exchange="none", with
                                 masks=masks, stage_lr=STAGE_LR, lr_factor=1.0, BA_cam_lr=0.001)
         opt.set_stage("color")
     it = MappingIteration(renderer, model, grids, frames, cams, H, W, FX, FY, CX, CY, pix_per_kf, "color", W_COLOR, generator=gen,
-                          arena=ar, exchange=exchange, optimizer=opt, shared_cameras=shared_cameras)
+                          arena=ar, exchange=exchange, optimizer=opt, shared_cameras=shared_cameras, world=world)
     return types.SimpleNamespace(P=P, bound=bound, model=model, grids=grids, renderer=renderer, frames=frames,
                                  frames_host=frames_host, poses=poses, cams=cams, gen=gen, arena=ar, optimizer=opt, masks=masks,
                                  iteration=it)
@@ -287,8 +287,6 @@ def run_ours(args):
                 "parallelism": (f"ray-shard dp{world}" if strong else f"keyframe-shard dp{world}"),
                 "optimizer_in_step": not args.no_optimizer, "gradient_exchange": exchange,
                 "frustum_voxels": {k: int(m.sum()) for k, m in (w.masks or {}).items()}}
-        if it._sparse is not None:
-            info["exchange_bytes_per_rank"] = it._sparse.bytes_per_rank()
 
         def after_step():
             for t in trained:
@@ -593,8 +591,11 @@ def run_ours(args):
                                "peak_source": which} if step_frac is not None else None),
             "sustained": sustained}
     if cfgname == "mapping" and getattr(w.iteration, "_sparse", None) is not None:
-        w.iteration._sparse.check_overflow()
-        line["config"]["touched_rows_this_rank"] = {k: int(c) for k, c in zip(w.iteration._sparse.keys, w.iteration._sparse.count.tolist())}
+        sp = w.iteration._sparse
+        sp.check_overflow()
+        line["config"]["exchange_send_buffer_bytes"] = sp.bytes_per_rank()
+        line["config"]["exchange_row_capacity"] = dict(sp.cap)
+        line["config"]["touched_rows_this_rank"] = {k: int(c) for k, c in zip(sp.keys, sp.count.tolist())}
     if rank == 0 and world == 1 and not args.light and cfgname == "mapping":
         line["cpu_baseline"] = cpu_baseline(budget_s=15.0)
         line["cpu_baseline_1thread"] = cpu_baseline(budget_s=8.0, threads=1, pix=200)

@@ -267,11 +267,11 @@ class SparseGradExchange:
     ``allreduce_gradients``).  No reference counterpart: the reference is single-GPU.
     """
 
-    def __init__(self, grid_shapes, tail_numel: int, device, cap_frac=0.25, mode: str = "allgather", group=None):
+    def __init__(self, grid_shapes, tail_numel: int, device, cap_frac=0.25, mode: str = "allgather", group=None, world=None):
         from . import _lib as L
         self.L = L
         self.device = torch.device(device)
-        self.world = world_size()
+        self.world = world_size() if world is None else int(world)
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.mode = mode
         self.keys = list(grid_shapes)

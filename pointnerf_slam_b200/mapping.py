@@ -32,12 +32,14 @@ class MappingIteration:
     def __init__(self, renderer, decoders, grids: Dict[str, torch.Tensor], frames: Sequence, cams: Sequence[torch.Tensor],
                  H, W, fx, fy, cx, cy, pix_per_frame: int, stage: str = "color", w_color: float = 0.2,
                  generator: Optional[torch.Generator] = None, arena: Optional[E.GradArena] = None,
-                 exchange: str = "none", optimizer=None, trained_decoders: Sequence[str] = ("color",), shared_cameras: bool = True):
+                 exchange: str = "none", optimizer=None, trained_decoders: Sequence[str] = ("color",), shared_cameras: bool = True,
+                 world: Optional[int] = None):
         """frames: [(depth (H,W) f32, colour (H,W,3))] device tensors, one per keyframe; cams: camera 7-vectors (those
         with requires_grad are bundle-adjusted).  exchange: 'none' | 'sparse' | 'sparse_p2p' | 'dense' | 'overlap' |
         'arena' -- how the gradients of a sharded batch are summed over the ranks (dist.py).  shared_cameras: True when
         every rank holds the same keyframes and the RAYS are sharded (pose gradients are summed too); False when the
-        KEYFRAMES are sharded (each camera's gradient stays on the rank that owns the keyframe)."""
+        KEYFRAMES are sharded (each camera's gradient stays on the rank that owns the keyframe).  world: number of ranks
+        the batch is sharded over (default: the process group's size; 1 = no collective at all)."""
         self.renderer, self.decoders, self.grids, self.frames, self.cams = renderer, decoders, grids, list(frames), list(cams)
         self.geom = (int(H), int(W), float(fx), float(fy), float(cx), float(cy))
         self.n, self.stage, self.w_color, self.gen = int(pix_per_frame), stage, float(w_color), generator
@@ -49,7 +51,7 @@ class MappingIteration:
         self.dec_params = [p for m in self.dec_modules.values() for p in m.parameters() if p.requires_grad]
         self.ba_cams = [c for c in self.cams if c.requires_grad]
         self.shared_cams = [c for c in self.ba_cams] if shared_cameras else []
-        self.world = D.world_size()
+        self.world = D.world_size() if world is None else int(world)
         self._sparse = None
         self._reducer = None
         self._tail_items = self.dec_params + self.shared_cams
@@ -57,12 +59,10 @@ class MappingIteration:
         for p in self._tail_items:                       # 16-byte aligned slots of the exchange's dense tail
             self._tail_off.append(tail)
             tail += (p.numel() + 3) // 4 * 4
-        if self.world > 1 or exchange.startswith("sparse"):
-            if exchange in ("sparse", "sparse_p2p"):
-                shapes = {k: grids[k].shape[2:] for k in self.grid_keys}
-                self._sparse = D.SparseGradExchange(shapes, tail, self.device, mode="p2p" if exchange == "sparse_p2p" else "allgather")
-            elif exchange in ("overlap", "arena"):
-                self._reducer = D.OverlappedGradReducer(arena if exchange == "arena" else None)
+        self.sparse_cap_frac = 0.15      # rows the exchange can carry per rank, as a fraction of all voxel rows
+        self._use_sparse = exchange in ("sparse", "sparse_p2p") and self.world > 1
+        if self.world > 1 and exchange in ("overlap", "arena"):
+            self._reducer = D.OverlappedGradReducer(arena if exchange == "arena" else None)
         self.last_indices: List[torch.Tensor] = []
 
     # ------------------------------------------------------------------------------------------
@@ -90,22 +90,61 @@ class MappingIteration:
             self.renderer.depth_max_override = None
         return mapping_loss(depth, color, gd, gc, self.stage, self.w_color)
 
+    @staticmethod
+    def _contiguous_block(tensors, numels):
+        """One flat float32 view over `tensors` if they lie back to back in memory (slots of numels[i] floats) inside the
+        same storage -- the gradient arena hands out its sinks that way -- else None."""
+        base = tensors[0].data_ptr()
+        off = 0
+        for t, n in zip(tensors, numels):
+            if t.dtype != torch.float32 or t.data_ptr() != base + 4 * off or t.untyped_storage().data_ptr() != tensors[0].untyped_storage().data_ptr():
+                return None
+            off += n
+        return torch.as_strided(tensors[0], (off,), (1,))
+
     def _exchange_sparse(self):
-        sp = self._sparse
-        tail = sp.tail_view()
-        views = [tail[o:o + p.numel()].view(p.shape) for o, p in zip(self._tail_off, self._tail_items)]
-        grads = [p.grad for p in self._tail_items]
-        torch._foreach_copy_(views, grads)
-        grid_grads = {}
+        """Sum the gradients over the ranks through dist.SparseGradExchange.  With the gradient arena the three grid
+        gradients are one contiguous [V_total][32] block and the decoder gradients one flat slice, so the whole exchange
+        is: pack (3 launches), tail copies, ONE all-gather (or none: P2P), apply, tail sums."""
+        grid_grads = []
         for k in self.grid_keys:
             g = self.grids[k].grad
             if not g.is_contiguous(memory_format=torch.channels_last_3d):
                 raise RuntimeError(f"{k}: sparse exchange needs the channels-last gradient the backward produces")
-            grid_grads[k] = g
-        summed = torch.empty_like(tail)
-        sp.exchange(grid_grads, summed)
+            grid_grads.append(g)
+        order = sorted(range(len(grid_grads)), key=lambda i: grid_grads[i].data_ptr())
+        flat_grids = self._contiguous_block([grid_grads[i] for i in order], [grid_grads[i].numel() for i in order])
+        pgrads = [p.grad for p in self.dec_params]
+        flat_params = self._contiguous_block(pgrads, [(p.numel() + 3) // 4 * 4 for p in self.dec_params]) if pgrads else None
+        if self._sparse is None:
+            if flat_grids is not None:
+                shapes = {"grids": (flat_grids.numel() // 32, 1, 1)}
+            else:
+                shapes = {k: self.grids[k].shape[2:] for k in self.grid_keys}
+            tail = sum((p.numel() + 3) // 4 * 4 for p in self._tail_items)
+            self._sparse = D.SparseGradExchange(shapes, tail, self.device, cap_frac=self.sparse_cap_frac,
+                                                mode="p2p" if self.exchange == "sparse_p2p" else "allgather", world=self.world)
+            self._sparse_flat = flat_grids is not None
+        sp = self._sparse
+        if self._sparse_flat != (flat_grids is not None):
+            raise RuntimeError("sparse exchange: the gradient buffers changed layout between iterations")
+        tail = sp.tail_view()
+        cam_grads = [c.grad for c in self.shared_cams]
+        n_par = sum((p.numel() + 3) // 4 * 4 for p in self.dec_params)
+        if flat_params is not None:
+            tail[:n_par].copy_(flat_params)
+        elif pgrads:
+            torch._foreach_copy_([tail[o:o + p.numel()].view(p.shape) for o, p in zip(self._tail_off, self.dec_params)], pgrads)
+        cam_views = [tail[o:o + c.numel()] for o, c in zip(self._tail_off[len(self.dec_params):], self.shared_cams)]
+        if cam_grads:
+            torch._foreach_copy_(cam_views, cam_grads)
+        summed = torch.empty_like(tail) if (flat_params is None or cam_grads) else None
+        if flat_params is not None and not cam_grads:
+            sp.exchange({"grids": flat_grids} if flat_grids is not None else dict(zip(self.grid_keys, grid_grads)), flat_params)
+            return
+        sp.exchange({"grids": flat_grids} if flat_grids is not None else dict(zip(self.grid_keys, grid_grads)), summed)
         outs = [summed[o:o + p.numel()].view(p.shape) for o, p in zip(self._tail_off, self._tail_items)]
-        torch._foreach_copy_(grads, outs)
+        torch._foreach_copy_(pgrads + cam_grads, outs)
 
     def __call__(self, indices=None) -> torch.Tensor:
         if self.arena is not None:
@@ -120,7 +159,7 @@ class MappingIteration:
                                      others=[c.grad for c in self.shared_cams])
             else:
                 loss.backward()
-                if self._sparse is not None:
+                if self._use_sparse:
                     self._exchange_sparse()
                 elif self.world > 1 and self.exchange == "dense":
                     D.allreduce_gradients([self.grids[k].grad for k in self.grid_keys] + [p.grad for p in self._tail_items])

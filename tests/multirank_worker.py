@@ -60,7 +60,8 @@ def main(out_path, exchange, sharding):
             cams0 = [c for x in ws for c in x.cams]
             full_idx = [all_idx[r][k] for r in range(world) for k in range(B.N_KEYFRAMES)]
             n_pix = pix
-        it = MappingIteration(w0.renderer, w0.model, w0.grids, frames, cams0, B.H, B.W, B.FX, B.FY, B.CX, B.CY, n_pix, "color", B.W_COLOR)
+        it = MappingIteration(w0.renderer, w0.model, w0.grids, frames, cams0, B.H, B.W, B.FX, B.FY, B.CX, B.CY, n_pix, "color", B.W_COLOR,
+                              world=1)
         it(full_idx)
         torch.cuda.synchronize()
         rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))

@@ -20,7 +20,7 @@ def _run(tmp_path, exchange, sharding, world=2):
     port = 29600 + os.getpid() % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multirank_worker.py"), out, exchange, sharding]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=150, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     return json.load(open(out))
 
