@@ -454,8 +454,10 @@ def run_ours(args):
         pipe["i"] += 1
         return out
 
-    # two-stream backward: a gain on one GPU; with gradient collectives in flight it loses -> on only for world == 1
-    par_bwd = os.environ.get("PN_PARALLEL_BACKWARD", "1" if world == 1 else "0") != "0"
+    # two-stream backward: a gain whenever no collective runs DURING the backward (one GPU, and the sparse exchanges, which
+    # start after it); with NCCL all-reduces of finished gradients in flight it loses (overlap / arena modes)
+    no_coll = world == 1 or (cfgname == "mapping" and os.environ.get("PN_BENCH_EXCHANGE", "sparse").startswith("sparse"))
+    par_bwd = os.environ.get("PN_PARALLEL_BACKWARD", "1" if no_coll else "0") != "0"
     E.PARALLEL_BACKWARD = par_bwd
 
     def timed(k, e2e, profile):

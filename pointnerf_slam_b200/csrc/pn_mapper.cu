@@ -539,33 +539,42 @@ struct SparseSrc { const uint32_t* bitmap; const uint32_t* prefix; const float* 
 constexpr int kMaxSrc = 16;
 struct SparseApplyArgs { SparseSrc src[kMaxSrc]; int nsrc; float* dense; int64_t V; int64_t cap; };
 
+// NS = compile-time bound on the number of sources.  Every load of a step (bitmap words, prefixes, then the up-to-NS
+// packed rows of one voxel row) is issued before the first add, so that with peer pointers the NVLink round trips
+// (~1 us each) of a step overlap instead of queueing behind one another; absent rows contribute an exact +0.
+template <int NS>
 __global__ void __launch_bounds__(256) k_rows_apply(const SparseApplyArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwords = (a.V + 31) >> 5;
   for (int64_t w = warp; w < nwords; w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
-    uint32_t words[kMaxSrc];
+    uint32_t words[NS], pref[NS];
     uint32_t any = 0;
 #pragma unroll
-    for (int s = 0; s < kMaxSrc; ++s) {
+    for (int s = 0; s < NS; ++s) {
       words[s] = s < a.nsrc ? a.src[s].bitmap[w] : 0u;
       any |= words[s];
     }
     if (!any) continue;
-#pragma unroll 1
+#pragma unroll
+    for (int s = 0; s < NS; ++s) pref[s] = words[s] ? a.src[s].prefix[w] : 0u;
+#pragma unroll 2
     for (int st = 0; st < 8; ++st) {
       const int rr = 4 * st + (lane >> 3);
       if (!((any >> rr) & 1u)) continue;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v[NS];
 #pragma unroll
-      for (int s = 0; s < kMaxSrc; ++s) {
-        if (s < a.nsrc && ((words[s] >> rr) & 1u)) {
-          const int64_t pos = (int64_t)a.src[s].prefix[w] + __popc(words[s] & ((1u << rr) - 1u));
-          if (pos < a.cap) {
-            const float4 v = reinterpret_cast<const float4*>(a.src[s].rows + pos * 32)[lane & 7];
-            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-          }
+      for (int s = 0; s < NS; ++s) {
+        v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((words[s] >> rr) & 1u) {
+          const int64_t pos = (int64_t)pref[s] + __popc(words[s] & ((1u << rr) - 1u));
+          if (pos < a.cap) v[s] = reinterpret_cast<const float4*>(a.src[s].rows + pos * 32)[lane & 7];
         }
+      }
+      float4 acc = v[0];
+#pragma unroll
+      for (int s = 1; s < NS; ++s) {
+        acc.x = __fadd_rn(acc.x, v[s].x); acc.y = __fadd_rn(acc.y, v[s].y); acc.z = __fadd_rn(acc.z, v[s].z); acc.w = __fadd_rn(acc.w, v[s].w);
       }
       reinterpret_cast<float4*>(a.dense + (w * 32 + rr) * 32)[lane & 7] = acc;
     }
@@ -747,7 +756,11 @@ extern "C" int pn_sparse_rows_apply(float* dense, int64_t V, int nsrc, const uin
   a.nsrc = nsrc; a.dense = dense; a.V = V; a.cap = cap;
   const int64_t nwords = (V + 31) / 32;
   const int grid = blocks_for(nwords, 8, 8 * sm_count());
-  k_rows_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nsrc <= 2) k_rows_apply<2><<<grid, 256, 0, st>>>(a);
+  else if (nsrc <= 4) k_rows_apply<4><<<grid, 256, 0, st>>>(a);
+  else if (nsrc <= 8) k_rows_apply<8><<<grid, 256, 0, st>>>(a);
+  else k_rows_apply<kMaxSrc><<<grid, 256, 0, st>>>(a);
   return launch_status("k_rows_apply");
 }
 
