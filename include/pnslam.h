@@ -153,6 +153,17 @@ int pn_image_rays_fwd(int H, int W, float fx, float fy, float cx, float cy, cons
 int pn_rays_bwd(const int64_t* idx, int n, int H0, int W0, int Wc, float fx, float fy, float cx, float cy,
                 const float* g_rays_o, const float* g_rays_d, float* g_c2w, void* stream);
 
+/* The Mapper's per-keyframe loop (src/Mapper.py:558-605: get_samples for every keyframe of the window, then cat) as
+ * ONE launch: idx (F,n) flat crop indices per keyframe, c2w (F,3,4) device, depth_ptrs / color_ptrs: DEVICE arrays of F
+ * device pointers to the keyframes' (H,W) depth and (H,W,3) colour images; outputs are the concatenated (F*n, ...) batch. */
+int pn_sample_rays_multi_fwd(const int64_t* idx, int F, int n, int H0, int W0, int Wc, int W, float fx, float fy,
+                             float cx, float cy, const float* c2w, const float* const* depth_ptrs,
+                             const void* const* color_ptrs, int color_is_f64, float* rays_o, float* rays_d,
+                             float* depth_out, void* color_out, void* stream);
+/* VJP: g_c2w (F,3,4) += per keyframe, as pn_rays_bwd; must be zeroed. */
+int pn_rays_multi_bwd(const int64_t* idx, int F, int n, int H0, int W0, int Wc, float fx, float fy, float cx, float cy,
+                      const float* g_rays_o, const float* g_rays_d, float* g_c2w, void* stream);
+
 /* -------- sample placement (src/utils/Renderer.py:82-175) -------- */
 
 /* Depth-guided + stratified z-values, sorted.  gt_depth may be NULL (then n_surface

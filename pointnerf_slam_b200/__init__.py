@@ -21,5 +21,5 @@ from . import _lib, engine, common, decoder, config, renderer, graphs, losses, m
 from .renderer import Renderer  # noqa: E402,F401
 from .decoder import NICE, MLP, MLP_no_xyz  # noqa: E402,F401
 from .config import get_model, load_bound, grid_init, attach_bounds  # noqa: E402,F401
-from .common import (get_samples, get_rays, get_rays_from_uv, get_camera_from_tensor,  # noqa: E402,F401
+from .common import (get_samples, get_samples_multi, KeyframeBatch, get_rays, get_rays_from_uv, get_camera_from_tensor,  # noqa: E402,F401
                      get_tensor_from_camera, raw2outputs_nerf_color, sample_pdf, normalize_3d_coordinate)

@@ -168,6 +168,74 @@ def get_samples(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, devi
     return ro, rd, d, c
 
 
+class _SampleRaysMultiFn(torch.autograd.Function):
+    """(F,3,4) poses + (F,n) pixel indices + F keyframe images -> the concatenated ray batch, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, c2w, idx, geom, depth_ptrs, color_ptrs, color_dtype):
+        H0, W0, Wc, W, fx, fy, cx, cy = geom
+        dev = c2w.device
+        F, n = idx.shape
+        c2wc = c2w.detach().float().contiguous()
+        ro = torch.empty((F * n, 3), dtype=torch.float32, device=dev)
+        rd = torch.empty((F * n, 3), dtype=torch.float32, device=dev)
+        d_out = torch.empty(F * n, dtype=torch.float32, device=dev)
+        c_out = torch.empty((F * n, 3), dtype=color_dtype, device=dev)
+        with L.device_guard(dev):
+            L.check(L.lib().pn_sample_rays_multi_fwd(C.c_void_p(idx.data_ptr()), F, n, H0, W0, Wc, W, f32(fx), f32(fy), f32(cx), f32(cy),
+                                                     C.c_void_p(c2wc.data_ptr()), C.c_void_p(depth_ptrs.data_ptr()),
+                                                     C.c_void_p(color_ptrs.data_ptr()), int(color_dtype == torch.float64),
+                                                     C.c_void_p(ro.data_ptr()), C.c_void_p(rd.data_ptr()), C.c_void_p(d_out.data_ptr()),
+                                                     C.c_void_p(c_out.data_ptr()), C.c_void_p(L.stream_ptr(dev))), "pn_sample_rays_multi_fwd")
+        ctx.geom, ctx.idx = geom, idx
+        ctx.mark_non_differentiable(d_out, c_out)
+        ctx.set_materialize_grads(False)
+        return ro, rd, d_out, c_out
+
+    @staticmethod
+    def backward(ctx, g_ro, g_rd, _gd, _gc):
+        H0, W0, Wc, W, fx, fy, cx, cy = ctx.geom
+        idx = ctx.idx
+        dev = idx.device
+        F, n = idx.shape
+        g = E.zeros((F, 3, 4), dev)
+        g_ro = g_ro.float().contiguous() if g_ro is not None else None
+        g_rd = g_rd.float().contiguous() if g_rd is not None else None
+        with L.device_guard(dev):
+            L.check(L.lib().pn_rays_multi_bwd(C.c_void_p(idx.data_ptr()), F, n, H0, W0, Wc, f32(fx), f32(fy), f32(cx), f32(cy),
+                                              C.c_void_p(L.ptr(g_ro)), C.c_void_p(L.ptr(g_rd)), C.c_void_p(g.data_ptr()),
+                                              C.c_void_p(L.stream_ptr(dev))), "pn_rays_multi_bwd")
+        return g, None, None, None, None, None
+
+
+class KeyframeBatch:
+    """The keyframes of a mapping window prepared for batched sampling: device arrays of the images' addresses (the
+    images themselves stay where the caller keeps them and may be overwritten in place between calls)."""
+
+    def __init__(self, frames, device):
+        self.depth = [d if (d.is_cuda and d.dtype == torch.float32 and d.is_contiguous()) else d.to(device).float().contiguous() for d, _ in frames]
+        self.color = [c if (c.is_cuda and c.is_contiguous() and c.dtype in (torch.float32, torch.float64)) else c.to(device).float().contiguous()
+                      for _, c in frames]
+        if len({c.dtype for c in self.color}) != 1:
+            raise RuntimeError("the keyframes' colour images must share one dtype")
+        self.color_dtype = self.color[0].dtype
+        self.depth_ptrs = torch.tensor([d.data_ptr() for d in self.depth], dtype=torch.int64, device=device)
+        self.color_ptrs = torch.tensor([c.data_ptr() for c in self.color], dtype=torch.int64, device=device)
+        self.F = len(frames)
+
+
+def get_samples_multi(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, batch: "KeyframeBatch", device, indices: Optional[torch.Tensor] = None):
+    """``get_samples`` (src/common.py:125-134) for every keyframe of a window at once and concatenated, i.e. the loop of
+    src/Mapper.py:558-605: c2w (F,3,4), indices (F,n) (default: ONE ``torch.randint`` draw of F*n values; callers that
+    must reproduce the reference's generator stream draw per keyframe and pass the indices, as mapping.MappingIteration does).  Returns rays_o, rays_d (F*n,3), depth (F*n,), colour (F*n,3); differentiable w.r.t. c2w."""
+    Hc, Wc = H1 - H0, W1 - W0
+    if indices is None:
+        indices = torch.randint(Hc * Wc, (batch.F, n), device=device)
+    indices = indices.to(device=device, dtype=torch.int64).contiguous()
+    geom = (int(H0), int(W0), int(Wc), int(W), float(fx), float(fy), float(cx), float(cy))
+    return _SampleRaysMultiFn.apply(c2w, indices, geom, batch.depth_ptrs, batch.color_ptrs, batch.color_dtype)
+
+
 class _ImageRaysFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, c2w, geom):

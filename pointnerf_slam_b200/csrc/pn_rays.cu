@@ -147,6 +147,65 @@ __global__ void __launch_bounds__(256) k_rays_bwd(const int64_t* __restrict__ id
   }
 }
 
+// ---- the same two kernels over F keyframes at once (blockIdx.y = keyframe): one launch for the Mapper's
+//      per-keyframe loop (src/Mapper.py:558-605) instead of one per keyframe
+template <typename CT>
+__global__ void k_sample_rays_multi(const int64_t* __restrict__ idx, int n, int H0, int W0, int Wc, int W, float fx, float fy,
+                                    float cx, float cy, const float* __restrict__ c2w, const float* const* __restrict__ depth,
+                                    const CT* const* __restrict__ color, float* __restrict__ ro, float* __restrict__ rd,
+                                    float* __restrict__ dout, CT* __restrict__ cout) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, f_ = blockIdx.y;
+  if (t >= n) return;
+  const int64_t o = (int64_t)f_ * n + t;
+  const int64_t f = idx[o];
+  const int r = (int)(f / Wc), c = (int)(f % Wc);
+  const int64_t pix = (int64_t)(H0 + r) * W + (W0 + c);
+  const float* dp = depth[f_];
+  const CT* cp = color[f_];
+  dout[o] = dp[pix];
+  cout[3 * o] = cp[3 * pix]; cout[3 * o + 1] = cp[3 * pix + 1]; cout[3 * o + 2] = cp[3 * pix + 2];
+  float d[3];
+  pixel_dir((float)(W0 + c), (float)(H0 + r), fx, fy, cx, cy, d);
+  rotate_dir(d, c2w + 12 * f_, 4, rd + 3 * o, ro + 3 * o);
+}
+
+__global__ void __launch_bounds__(256) k_rays_bwd_multi(const int64_t* __restrict__ idx, int n, int H0, int W0, int Wc, float fx,
+                                                       float fy, float cx, float cy, const float* __restrict__ go,
+                                                       const float* __restrict__ gd, float* __restrict__ gc2w) {
+  __shared__ float red[8][12];
+  const int f_ = blockIdx.y;
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int64_t o = (int64_t)f_ * n + t;
+    const int64_t f = idx[o];
+    const int r = (int)(f / Wc), c = (int)(f % Wc);
+    float d[3];
+    pixel_dir((float)(W0 + c), (float)(H0 + r), fx, fy, cx, cy, d);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float g = gd ? gd[3 * o + a] : 0.f;
+      acc[4 * a] = fmaf(g, d[0], acc[4 * a]);
+      acc[4 * a + 1] = fmaf(g, d[1], acc[4 * a + 1]);
+      acc[4 * a + 2] = fmaf(g, d[2], acc[4 * a + 2]);
+      acc[4 * a + 3] += go ? go[3 * o + a] : 0.f;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const float s = warp_sum(acc[k]);
+    if (lane == 0) red[warp][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(gc2w + 12 * f_ + threadIdx.x, s);
+  }
+}
+
 // ------------------------------------------------------------------ z-values
 __device__ __forceinline__ void insertion_sort(double* z, int n) {
   for (int i = 1; i < n; ++i) {
@@ -827,6 +886,36 @@ extern "C" int pn_sample_rays_fwd(const int64_t* idx, int n, int H0, int W0, int
     k_sample_rays<float><<<g, 128, 0, PN_ST>>>(idx, n, H0, W0, Wc, W, fx, fy, cx, cy, c2w, c2w_ld, depth_img,
                                                (const float*)color_img, rays_o, rays_d, depth_out, (float*)color_out);
   return launch_status("k_sample_rays");
+}
+
+extern "C" int pn_sample_rays_multi_fwd(const int64_t* idx, int F, int n, int H0, int W0, int Wc, int W, float fx, float fy,
+                                       float cx, float cy, const float* c2w, const float* const* depth_ptrs,
+                                       const void* const* color_ptrs, int color_is_f64, float* rays_o, float* rays_d,
+                                       float* depth_out, void* color_out, void* stream) {
+  if (!idx || !c2w || !depth_ptrs || !color_ptrs || !rays_o || !rays_d || !depth_out || !color_out || F <= 0 || F > 65535 || n < 0 ||
+      Wc <= 0) {
+    set_error("pn_sample_rays_multi_fwd: bad arguments");
+    return 1;
+  }
+  if (n == 0) return 0;
+  const dim3 g((n + 127) / 128, F);
+  if (color_is_f64)
+    k_sample_rays_multi<double><<<g, 128, 0, PN_ST>>>(idx, n, H0, W0, Wc, W, fx, fy, cx, cy, c2w, depth_ptrs,
+                                                      (const double* const*)color_ptrs, rays_o, rays_d, depth_out, (double*)color_out);
+  else
+    k_sample_rays_multi<float><<<g, 128, 0, PN_ST>>>(idx, n, H0, W0, Wc, W, fx, fy, cx, cy, c2w, depth_ptrs,
+                                                     (const float* const*)color_ptrs, rays_o, rays_d, depth_out, (float*)color_out);
+  return launch_status("k_sample_rays_multi");
+}
+
+extern "C" int pn_rays_multi_bwd(const int64_t* idx, int F, int n, int H0, int W0, int Wc, float fx, float fy, float cx, float cy,
+                                 const float* g_rays_o, const float* g_rays_d, float* g_c2w, void* stream) {
+  if (!idx || !g_c2w || F <= 0 || F > 65535 || n < 0 || Wc <= 0) { set_error("pn_rays_multi_bwd: bad arguments"); return 1; }
+  if (n == 0) return 0;
+  int gx = (n + 255) / 256;
+  if (gx > 8) gx = 8;
+  k_rays_bwd_multi<<<dim3(gx, F), 256, 0, PN_ST>>>(idx, n, H0, W0, Wc, fx, fy, cx, cy, g_rays_o, g_rays_d, g_c2w);
+  return launch_status("k_rays_bwd_multi");
 }
 
 extern "C" int pn_image_rays_fwd(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,

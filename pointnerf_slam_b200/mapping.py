@@ -21,7 +21,7 @@ import torch
 
 from . import dist as D
 from . import engine as E
-from .common import get_camera_from_tensor, get_samples
+from .common import KeyframeBatch, get_camera_from_tensor, get_samples_multi
 from .losses import mapping_loss
 
 TRAINED_GRIDS = {"coarse": ("grid_coarse",), "middle": ("grid_middle",), "fine": ("grid_middle", "grid_fine"),
@@ -63,23 +63,30 @@ class MappingIteration:
         self._use_sparse = exchange in ("sparse", "sparse_p2p") and self.world > 1
         if self.world > 1 and exchange in ("overlap", "arena"):
             self._reducer = D.OverlappedGradReducer(arena if exchange == "arena" else None)
-        self.last_indices: List[torch.Tensor] = []
+        self.last_indices = None
+        self._batch: Optional[KeyframeBatch] = None
 
     # ------------------------------------------------------------------------------------------
     def trained(self) -> List[torch.Tensor]:
         return [self.grids[k] for k in self.grid_keys] + self.dec_params + self.ba_cams
 
-    def sample(self, indices: Optional[Sequence[torch.Tensor]] = None):
+    def sample(self, indices=None):
+        """The per-keyframe loop of Mapper.py:558-605 as one batched launch: camera tensors -> poses, pixel indices (one
+        ``torch.randint`` call per keyframe, in keyframe order, so the generator stream is the reference's), rays, depths and
+        colours of all keyframes concatenated.  `indices`: (F,n) tensor or a list of F index tensors to replay a draw."""
         H, W, fx, fy, cx, cy = self.geom
-        ro, rd, gd, gc = [], [], [], []
-        self.last_indices = []
-        for k, (depth, color) in enumerate(self.frames):
-            c2w = get_camera_from_tensor(self.cams[k])
-            idx = indices[k] if indices is not None else torch.randint(H * W, (self.n,), device=self.device, generator=self.gen)
-            self.last_indices.append(idx)
-            o, d, dd, cc = get_samples(0, H, 0, W, self.n, H, W, fx, fy, cx, cy, c2w, depth, color, self.device, indices=idx)
-            ro.append(o); rd.append(d); gd.append(dd); gc.append(cc)
-        return torch.cat(ro), torch.cat(rd), torch.cat(gd), torch.cat(gc)
+        F = len(self.frames)
+        if self._batch is None:
+            self._batch = KeyframeBatch(self.frames, self.device)
+        if indices is None:
+            idx = torch.empty((F, self.n), dtype=torch.int64, device=self.device)
+            for k in range(F):
+                torch.randint(H * W, (self.n,), device=self.device, generator=self.gen, out=idx[k])
+        else:
+            idx = indices if isinstance(indices, torch.Tensor) else torch.stack([i.to(self.device) for i in indices])
+        self.last_indices = idx
+        c2w = get_camera_from_tensor(torch.stack(self.cams))
+        return get_samples_multi(0, H, 0, W, self.n, H, W, fx, fy, cx, cy, c2w, self._batch, self.device, indices=idx)
 
     def forward_loss(self, indices=None):
         ro, rd, gd, gc = self.sample(indices)

@@ -222,3 +222,30 @@ def test_sparse_rows_roundtrip_and_ordered_sum():
     o = torch.empty(1001, device=DEV)
     L.check(lib.pn_dense_sum(C.c_void_p(o.data_ptr()), C.c_int64(1001), 3, arr(srcs), st), "sum")
     assert torch.equal(o, (srcs[0] + srcs[1]) + srcs[2])
+
+
+def test_batched_keyframe_sampling_equals_the_per_keyframe_loop():
+    """get_samples_multi (one launch for the Mapper's per-keyframe loop, Mapper.py:558-605) == get_samples per keyframe + cat,
+    bit for bit, forward and pose gradient; float64 colour images as the reference's dataset path delivers them."""
+    import pointnerf_slam_b200 as P
+    gen = torch.Generator().manual_seed(4)
+    F, n = 3, 257
+    cams = [torch.randn(7, generator=gen).to(DEV).requires_grad_(True) for _ in range(F)]
+    cams2 = [c.detach().clone().requires_grad_(True) for c in cams]
+    for dtype in (torch.float32, torch.float64):
+        frames = [(synthetic_depth(60 + k).to(DEV), torch.rand(H, W, 3, generator=gen).to(dtype).to(DEV)) for k in range(F)]
+        idx = torch.randint((H - 40) * (W - 60), (F, n), generator=gen).to(DEV)
+        c2w = P.get_camera_from_tensor(torch.stack(cams))
+        out = P.get_samples_multi(20, H - 20, 30, W - 30, n, H, W, FX, FY, CX, CY, c2w, P.KeyframeBatch(frames, DEV), DEV, indices=idx)
+        ref = [P.get_samples(20, H - 20, 30, W - 30, n, H, W, FX, FY, CX, CY, P.get_camera_from_tensor(cams2[k]), frames[k][0], frames[k][1],
+                             DEV, indices=idx[k]) for k in range(F)]
+        for j in range(4):
+            assert torch.equal(out[j], torch.cat([r[j] for r in ref])), j
+        assert out[3].dtype == dtype
+        wgt = torch.randn(F * n, 3, generator=gen).to(DEV)
+        for c in cams + cams2:
+            c.grad = None
+        ((out[0] * wgt).sum() + (out[1] * wgt.flip(0)).sum()).backward()
+        (sum((r[0] * wgt[k * n:(k + 1) * n]).sum() for k, r in enumerate(ref)) + sum((r[1] * wgt.flip(0)[k * n:(k + 1) * n]).sum() for k, r in enumerate(ref))).backward()
+        for a, b in zip(cams, cams2):
+            assert T.rel_max(a.grad, b.grad) < 1e-5
