@@ -110,3 +110,63 @@ def test_reserve_sms_round_trip():
         assert lib.pn_reserve_sms(0) == 0
     finally:
         lib.pn_reserve_sms(prev)
+
+
+def test_product_scene_setup_matches_oracle_bit_for_bit():
+    """config.load_bound / grid_shapes / grid_init (src/NICE_SLAM.py:200-315): the PRODUCT's functions, not only the
+    oracle's, against the reference values (float32 rounding of the enlarged bound, truncated z extent, x<->z swap)."""
+    from oracle import nice_oracle as O
+    import bench as B
+    bound = P.load_bound(B.CFG)
+    ref = O.scene_bound(B.CFG["mapping"]["bound"], 1.0, 0.32)
+    assert bound.dtype == torch.float64 and torch.equal(bound, ref)
+    assert bound[:, 1].tolist() == [8.94000015258789, 5.7600000381469725, 3.5399999618530273]
+    shapes = P.config.grid_shapes(B.CFG, bound)
+    assert shapes == {"grid_coarse": (7, 8, 11), "grid_middle": (21, 28, 37), "grid_fine": (43, 56, 74), "grid_color": (43, 56, 74)}
+    assert shapes == O.grid_shapes(ref, B.CFG["grid_len"])
+    grids = P.grid_init(B.CFG, bound, "cpu", generator=torch.Generator().manual_seed(1))
+    og = O.init_grids(ref, B.CFG["grid_len"], 32, 2, True, torch.Generator().manual_seed(1))
+    for k, g in grids.items():
+        assert g.shape == (1, 32) + shapes[k] and g.is_contiguous(memory_format=torch.channels_last_3d)
+        assert torch.equal(g, og[k]), k                     # same values in the reference's logical (1,C,Z,Y,X) order
+    assert float(grids["grid_fine"].std()) < 2e-4 < float(grids["grid_middle"].std())
+    # a bound that is already a multiple of 0.32 still grows by one cell (NICE_SLAM.py:211: int(...)+1)
+    cfg2 = dict(B.CFG, mapping={"bound": [[0.0, 0.64], [0.0, 0.32], [-0.32, 0.32]]})
+    assert torch.equal(P.load_bound(cfg2), O.scene_bound(cfg2["mapping"]["bound"], 1.0, 0.32))
+
+
+def test_get_tensor_from_camera_round_trip():
+    """common.get_tensor_from_camera (src/common.py:179-201; host-side Shepperd conversion instead of mathutils): every
+    branch of the conversion, [w,x,y,z] order with w >= 0, Tquad order, and the inverse through the oracle's
+    camera_from_tensor."""
+    import numpy as np
+    from scipy.spatial.transform import Rotation
+    from oracle import nice_oracle as O
+    rots = [Rotation.from_euler("xyz", a).as_matrix() for a in ([0.1, -0.2, 0.3], [3.0, 0.1, 0.0], [0.1, 3.0, 0.2], [0.2, 0.1, 3.1],
+                                                                [2.0, 2.0, 2.0], [0, 0, 0])]
+    for i, R in enumerate(rots):
+        RT = np.eye(4)
+        RT[:3, :3], RT[:3, 3] = R, [0.5 * i, -1.0, 2.0]
+        t = P.get_tensor_from_camera(torch.from_numpy(RT).float())
+        assert t.shape == (7,) and t.dtype == torch.float32 and float(t[0]) >= 0.0
+        q = Rotation.from_matrix(R).as_quat()               # scipy: [x,y,z,w]
+        qs = np.array([q[3], q[0], q[1], q[2]])
+        qs = -qs if qs[0] < 0 else qs
+        assert np.allclose(t[:4].numpy(), qs, atol=1e-6) or np.allclose(t[:4].numpy(), -qs, atol=1e-6)
+        assert np.allclose(t[4:].numpy(), RT[:3, 3], atol=1e-7)
+        back = O.camera_from_tensor(t.double())
+        assert np.allclose(back.numpy(), RT[:3, :4], atol=1e-6)
+        tq = P.get_tensor_from_camera(RT[:3], Tquad=True)
+        assert torch.allclose(tq[:3], t[4:]) and torch.allclose(tq[3:], t[:4])
+
+
+def test_mapper_side_entry_points_fail_loudly_on_cpu():
+    import pointnerf_slam_b200.mapper as PM
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PM.frustum_voxel_mask(torch.eye(4), "grid_fine", (4, 4, 4), torch.zeros(8, 8), torch.tensor([[0.0, 1.0]] * 3), 8, 8, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PM.StageOptimizer({"grid_middle": torch.zeros(1, 32, 2, 2, 2)}, [], [])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PM.prefilter_mask(torch.zeros(4, 3), torch.ones(4, 3), torch.ones(4), torch.tensor([[0.0, 1.0]] * 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PM.select_depth_pixels(torch.zeros(8, 8), 0, 8, 0, 8)
