@@ -32,6 +32,11 @@ int launch_wgrad_tc32(int64_t N, int n_out, const float* H, const float* C, cons
                       const float* GO, const float* P32, const uint32_t* relu_bits, float* const* W, float* const* b,
                       float* const* Wc, float* const* bc, float* Wo, float* bo, float* B, cudaStream_t st);
 
+// tensor-core GEMM of the iMAP* MLP (pn_imap_tc.cu): 0 ok, 1 error, -1 not applicable.  ep: 0 store, 1 bias+relu,
+// 2 relu mask (aux), 3 split-K atomics (a_rowsum: optional, += sum_k A(m,k): the bias gradient rides in the weight-gradient GEMM)
+int tc_gemm(int ep, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
+            int64_t M, int N, int64_t K, const float* bias, const float* aux, int splitk, float* a_rowsum, cudaStream_t st);
+
 // ---- programmatic dependent launch ------------------------------------------------------------
 // The persistent decoder kernels start with a prologue that does not depend on the previous kernel
 // of the stream (weights -> shared memory, TMEM allocation).  Launched with the programmatic-

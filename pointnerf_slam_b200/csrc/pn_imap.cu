@@ -1,11 +1,12 @@
 // iMAP* single-MLP decoder (decoder.MLP with c_dim = 0: Fourier-93 -> n_blocks x
 // hidden relu layers -> 4 outputs; src/conv_onet/config.py:28-32,
 // src/conv_onet/models/decoder.py:189-203).  At hidden 256 the layers are real
-// GEMMs ([N x 256] . [256 x 256]), so the path is a chain of tiled FP32 GEMM
-// launches with fused epilogues (bias+relu, relu-mask, split-K atomics) over
-// row-major activations kept in HBM (1 KB per sample and layer; arithmetic
-// intensity 64 FLOP/B, i.e. compute bound), plus small kernels for the
-// embedding and the 4-wide output layer.
+// GEMMs ([N x 256] . [256 x 256]), so the path is a chain of GEMM launches with
+// fused epilogues (bias+relu, relu-mask, split-K atomics) over row-major
+// activations kept in HBM (1 KB per sample and layer), plus small kernels for the
+// embedding and the 4-wide output layer.  The GEMMs run on the tensor cores
+// (tcgen05, 3xTF32; pn_imap_tc.cu); the FFMA tiles below serve the slivers
+// (4- and 3-row weight gradients) and odd shapes.
 #include "pn_common.cuh"
 
 namespace pn {
@@ -92,6 +93,16 @@ int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
   dim3 grid((N + TN - 1) / TN, (unsigned)((M + TM - 1) / TM), EP == EP_ATOMIC ? splitk : 1);
   k_sgemm<EP><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, aux);
   return launch_status("k_sgemm");
+}
+
+// the layer GEMMs: tensor cores (pn_imap_tc.cu) whenever the shape fills 128-row tiles, the FFMA tiles for the slivers
+// (dWo: 4 rows, dB: 3 rows)
+template <int EP>
+int gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
+         int64_t M, int N, int64_t K, const float* bias, const float* aux, int splitk, cudaStream_t st) {
+  const int rc = tc_gemm(EP, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, aux, splitk, nullptr, st);
+  if (rc >= 0) return rc;
+  return sgemm<EP>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, aux, splitk, st);
 }
 
 // E[n][96] = sin(p . B[:,k]) (cols 93..95 = 0); optionally P32 [3][N]
@@ -236,7 +247,7 @@ extern "C" int pn_imap_mlp_fwd(const pn_points* pts, const pn_imap_mlp* w, const
     const int K = l == 0 ? PN_EMBED : hid;
     const int ldx = l == 0 ? 96 : hid;
     // Y = relu(X . W^T + b): B(k,n) = W[n*K + k]
-    if (sgemm<EP_BIAS_RELU>(X, ldx, 1, w->W[l], 1, K, H + (int64_t)l * N * hid, hid, N, hid, K, w->b[l], nullptr, 1, st)) return 1;
+    if (gemm<EP_BIAS_RELU>(X, ldx, 1, w->W[l], 1, K, H + (int64_t)l * N * hid, hid, N, hid, K, w->b[l], nullptr, 1, st)) return 1;
   }
   k_imap_out<<<wg, 256, 0, st>>>(*pts, mb, mb, apply_mask, H + (int64_t)(w->n_blocks - 1) * N * hid, hid, w->Wo, w->bo, raw);
   return launch_status("k_imap_out");
@@ -270,16 +281,21 @@ extern "C" int pn_imap_mlp_bwd(const pn_points* pts, const pn_imap_mlp* w, const
     const float* X = l == 0 ? E : H + (int64_t)(l - 1) * N * hid;
     const int K = l == 0 ? PN_EMBED : hid;
     const int ldx = l == 0 ? 96 : hid;
-    if (g && g->W[l])  // dW_l (hid x K) = cur^T . X : A(m,k) = cur[k*hid + m], B(k,n) = X[k*ldx + n]
-      if (sgemm<EP_ATOMIC>(cur, 1, hid, X, ldx, 1, g->W[l], K, hid, K, N, nullptr, nullptr, splitk, st)) return 1;
-    if (g && g->b[l]) { k_colsum<<<dim3((hid + 31) / 32, 32), 256, 0, st>>>(cur, N, hid, hid, g->b[l]); if (launch_status("k_colsum")) return 1; }
+    bool bias_done = false;
+    if (g && g->W[l]) {  // dW_l (hid x K) = cur^T . X : A(m,k) = cur[k*hid + m], B(k,n) = X[k*ldx + n]; db_l rides along
+      const int rc = tc_gemm(EP_ATOMIC, cur, 1, hid, X, ldx, 1, g->W[l], K, hid, K, N, nullptr, nullptr, splitk, g->b[l], st);
+      if (rc > 0) return 1;
+      if (rc == 0) bias_done = g->b[l] != nullptr;
+      else if (sgemm<EP_ATOMIC>(cur, 1, hid, X, ldx, 1, g->W[l], K, hid, K, N, nullptr, nullptr, splitk, st)) return 1;
+    }
+    if (g && g->b[l] && !bias_done) { k_colsum<<<dim3((hid + 31) / 32, 32), 256, 0, st>>>(cur, N, hid, hid, g->b[l]); if (launch_status("k_colsum")) return 1; }
     if (l > 0) {  // next = (cur . W_l) masked by H_{l-1} > 0 : B(k,n) = W[k*K + n]
-      if (sgemm<EP_MASK>(cur, hid, 1, w->W[l], K, 1, nxt, hid, N, hid, hid, nullptr, X, 1, st)) return 1;
+      if (gemm<EP_MASK>(cur, hid, 1, w->W[l], K, 1, nxt, hid, N, hid, hid, nullptr, X, 1, st)) return 1;
       float* t = cur; cur = nxt; nxt = t;
     } else if (g_pts || (g && g->B)) {
       // GE (N x 96) = cur . W_0 (hid x 93); then * cos(arg), dp, dB
       float* GE = nxt;  // reuse as N x 96 (hid >= 96 is not required: buffers are sized max(hid,96))
-      if (sgemm<EP_STORE>(cur, hid, 1, w->W[0], PN_EMBED, 1, GE, 96, N, PN_EMBED, hid, nullptr, nullptr, 1, st)) return 1;
+      if (gemm<EP_STORE>(cur, hid, 1, w->W[0], PN_EMBED, 1, GE, 96, N, PN_EMBED, hid, nullptr, nullptr, 1, st)) return 1;
       k_imap_embed_bwd<<<wg, 256, 0, st>>>(*pts, mb, mb, w->B, GE, g_pts);
       if (launch_status("k_imap_embed_bwd")) return 1;
       if (g && g->B)  // dB (3 x 93) = P^T . GE : A(m,k) = P32[m*N + k], B(k,n) = GE[k*96 + n]
