@@ -95,6 +95,29 @@ int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
   return launch_status("k_sgemm");
 }
 
+// Thin weight gradients (dWo: 4 rows, dB: 3 rows): out[r][c] += sum_n A(r,n) * X[n*ldx + c], A(r,n) = A[r*sar + n*san].
+// Thread = column (coalesced reads of X's rows), R accumulators in registers, one atomicAdd per thread and row: X is read
+// once at streaming speed instead of going through 64-row GEMM tiles that would be 94 % padding.
+template <int R>
+__global__ void __launch_bounds__(256) k_thin_wgrad(const float* __restrict__ A, int64_t sar, int64_t san, const float* __restrict__ X,
+                                                    int64_t ldx, int64_t N, int C, float* __restrict__ out, int ldo) {
+  const int c = threadIdx.x;
+  const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t n0 = (int64_t)blockIdx.x * per, n1 = n0 + per < N ? n0 + per : N;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (c < C) {
+    for (int64_t n = n0; n < n1; ++n) {
+      const float x = X[n * ldx + c];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(__ldg(A + r * sar + n * san), x, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) atomicAdd(out + r * ldo + c, acc[r]);
+  }
+}
+
 // the layer GEMMs: tensor cores (pn_imap_tc.cu) whenever the shape fills 128-row tiles, the FFMA tiles for the slivers
 // (dWo: 4 rows, dB: 3 rows)
 template <int EP>
@@ -274,8 +297,12 @@ extern "C" int pn_imap_mlp_bwd(const pn_points* pts, const pn_imap_mlp* w, const
   float* nxt = GB;
   k_imap_out_bwd<<<wg, 256, 0, st>>>(*pts, mb, mb, apply_mask, g_raw, Hlast, hid, w->Wo, GO, cur);
   if (launch_status("k_imap_out_bwd")) return 1;
-  if (g && g->Wo)  // dWo (4 x hid) = GO^T . H_last
-    if (sgemm<EP_ATOMIC>(GO, 1, 4, Hlast, hid, 1, g->Wo, hid, 4, hid, N, nullptr, nullptr, splitk, st)) return 1;
+  if (g && g->Wo) {  // dWo (4 x hid) = GO^T . H_last
+    if (hid <= 256) {
+      k_thin_wgrad<4><<<4 * sm_count(), 256, 0, st>>>(GO, 1, 4, Hlast, hid, N, hid, g->Wo, hid);
+      if (launch_status("k_thin_wgrad")) return 1;
+    } else if (sgemm<EP_ATOMIC>(GO, 1, 4, Hlast, hid, 1, g->Wo, hid, 4, hid, N, nullptr, nullptr, splitk, st)) return 1;
+  }
   if (g && g->bo) { k_colsum<<<dim3(1, 64), 256, 0, st>>>(GO, N, 4, 4, g->bo); if (launch_status("k_colsum")) return 1; }
   for (int l = nb - 1; l >= 0; --l) {
     const float* X = l == 0 ? E : H + (int64_t)(l - 1) * N * hid;
@@ -298,8 +325,10 @@ extern "C" int pn_imap_mlp_bwd(const pn_points* pts, const pn_imap_mlp* w, const
       if (gemm<EP_STORE>(cur, hid, 1, w->W[0], PN_EMBED, 1, GE, 96, N, PN_EMBED, hid, nullptr, nullptr, 1, st)) return 1;
       k_imap_embed_bwd<<<wg, 256, 0, st>>>(*pts, mb, mb, w->B, GE, g_pts);
       if (launch_status("k_imap_embed_bwd")) return 1;
-      if (g && g->B)  // dB (3 x 93) = P^T . GE : A(m,k) = P32[m*N + k], B(k,n) = GE[k*96 + n]
-        if (sgemm<EP_ATOMIC>(P32, N, 1, GE, 96, 1, g->B, PN_EMBED, 3, PN_EMBED, N, nullptr, nullptr, splitk, st)) return 1;
+      if (g && g->B) {  // dB (3 x 93) = P^T . GE : A(r,n) = P32[r*N + n]
+        k_thin_wgrad<3><<<4 * sm_count(), 256, 0, st>>>(P32, N, 1, GE, 96, N, PN_EMBED, g->B, PN_EMBED);
+        if (launch_status("k_thin_wgrad")) return 1;
+      }
     }
   }
   return 0;
