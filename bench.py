@@ -365,7 +365,8 @@ def run_ours(args):
             units_total, unit, bytes_per_unit = H * W, "rays/s", BYTES_PER_RAY_DENSE
             metric = "rays/sec render_img (dense full-frame render, no grad, stage color)"
             pinned, dev_in = [fh[0].pin_memory()], [depth]
-            n_s = (H * W // world) * S
+            n_chunks = -(-H * W // renderer.ray_batch_size)   # one launch per decoder and 100k-ray chunk: bytes of the AVERAGE launch
+            n_s = (H * W // world) * S // n_chunks
             alg = {f"grid_mlp_fwd:{k}": n_s * (2048 if k == "fine" else 1024) for k in ("color", "fine", "middle")}
             info = {"workload": "dense_render: render_img of one 680x1200 frame = 816,000 rays x 48 samples in the reference's "
                                 "100k-ray chunks; each chunk's rays shard over the ranks, outputs all-gathered",

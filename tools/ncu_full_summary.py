@@ -11,7 +11,10 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+           "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "lts__t_sectors_op_red.sum",
+           "lts__t_sectors_op_atom.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
 UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
 
 
@@ -24,6 +27,8 @@ def main(rep, out_txt, out_json, header):
         name = r[hdr.index("Kernel Name")]
         lines.append(f"--- {name}")
         for m in METRICS:
+            if m not in hdr:
+                continue
             i = hdr.index(m)
             lines.append(f"   {m:90s} {r[i]:>14s} {units[i]}")
         short = re.sub(r"\(.*", "", name).replace("void ", "").replace("unnamed>::", "").strip()
