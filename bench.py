@@ -73,7 +73,21 @@ BYTES_PER_RAY_TRACK = 294_960       # fwd+bwd tracking (re-gather, no scatter)
 BYTES_PER_RAY_DENSE = 147_504       # fwd only, stage colour
 BYTES_PER_POINT_MESH = 2_076        # eval_points stage fine
 BYTES_PER_SAMPLE_GATHER = 1024
+# k-NN aggregation (config 4, builder-defined): per sample, forward = 8 x (16 B position record + 128 B feature row) + 128 B blended
+# feature + 64 B index / distance lists; backward = 128 B feature gradient + 64 B lists + 8 x (128 B row + 12 B position) for the
+# point gradient + 8 x 256 B read-modify-write of the gradient rows + 12 B point gradient
+BYTES_PER_SAMPLE_KNN_FWD = 8 * (16 + 128) + 128 + 64
+BYTES_PER_SAMPLE_KNN_BWD = 128 + 64 + 8 * (128 + 12) + 8 * 256 + 12
+BYTES_PER_RAY_KNN = 48 * (BYTES_PER_SAMPLE_KNN_FWD + BYTES_PER_SAMPLE_KNN_BWD)
+KNN_RADIUS = 0.16
 METRIC = "rays/sec fwd+bwd render_batch_ray (NICE mapping iteration, stage color)"
+
+
+ROOFLINE_NOTE = ("decoder layers run on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulate in TMEM); the decoder kernels are "
+                 "latency/issue-bound (tensor pipe 10-16% active, 16-24 warps/SM), not HBM-bound; the grids (46 MiB) are L2-resident, "
+                 "so DRAM traffic is far below the algorithmic bytes; HBM roofline is the BASELINE.md denominator")
+ROOFLINE_NOTE_KNN = ("integer/float32 search + gather: no GEMM, SIMT kernels only; the candidate scan of the 27 neighbouring cells "
+                     "(~150 position records per sample, L1/L2 hits) is not part of the algorithmic bytes")
 
 
 def workload_name(scaling="weak"):
@@ -353,6 +367,59 @@ def run_ours(args):
         after_step = lambda: None
         graph_gens = [gen]
         result_of = lambda out: out
+    elif cfgname == "knn":
+        # BASELINE config 4 (builder-defined semantics): 1,048,576 neural points U(bound), 32-ch features
+        # N(0, 0.01^2), K = 8, the 5000-ray x 48-sample batch of the mapping step; fwd + bwd into features and camera pose
+        from pointnerf_slam_b200 import knn as PK
+        P_, bound, model, grids, renderer = build_scene(dev, True)
+        fh = synthetic_frames(1, 100 + rank)[0]
+        depth, color = fh[0].to(dev), fh[1].to(dev)
+        pose = keyframe_poses(rank)[0].to(dev)
+        cam = P.get_tensor_from_camera(pose).to(dev).requires_grad_(True)
+        gen = torch.Generator(device=dev).manual_seed(79 + rank)
+        gp = torch.Generator().manual_seed(4)
+        b32 = bound.to(torch.float32)
+        n_pts = 1 << 20
+        xyz = (b32[:, 0] + (b32[:, 1] - b32[:, 0]) * torch.rand((n_pts, 3), generator=gp)).clamp(b32[:, 0], b32[:, 1]).contiguous().to(dev)
+        feat = (0.01 * torch.randn((n_pts, 32), generator=gp)).to(dev).requires_grad_(True)
+        field = PK.NeuralPointField(xyz, feat, bound, KNN_RADIUS, 1e-6)
+        gw = torch.randn((5000 * S, 32), generator=gp).to(dev)          # stands in for the decoder's feature gradient
+
+        def step_body():
+            c = P.get_camera_from_tensor(cam)
+            idx = torch.randint(H * W, (5000,), device=dev, generator=gen)
+            o, d, gd, gc = P.get_samples(0, H, 0, W, 5000, H, W, FX, FY, CX, CY, c, depth, color, dev, indices=idx)
+            z = renderer.sample_z(d, o, gd)
+            f = field.aggregate_rays(o, d, z)
+            loss = (f * gw).sum()
+            cam.grad = None
+            feat.grad = None
+            loss.backward()
+            if world > 1:
+                dist.all_reduce(feat.grad)
+            return loss
+
+        def knn_cpu():
+            with torch.no_grad():
+                idx = torch.randint(H * W, (5000,), device=dev, generator=gen)
+                o, d, gd, gc = P.get_samples(0, H, 0, W, 5000, H, W, FX, FY, CX, CY, pose, depth, color, dev, indices=idx)
+                z = renderer.sample_z(d, o, gd)
+                p = (o.double()[:, None, :] + d.double()[:, None, :] * z[..., None]).reshape(-1, 3).float().cpu()
+            return knn_cpu_baseline(xyz.cpu(), feat.detach().cpu(), p, gw.cpu(), KNN_RADIUS)
+        pinned = [fh[0].pin_memory(), fh[1].pin_memory()]
+        dev_in = [depth, color]
+        units_rank, unit, bytes_per_unit = 5000, "rays/s", BYTES_PER_RAY_KNN
+        metric = "rays/sec fwd+bwd k-NN neural-point feature aggregation (1,048,576 points, K=8, 48 samples/ray)"
+        n_samples = 5000 * S
+        alg = {"knn_fwd": n_samples * BYTES_PER_SAMPLE_KNN_FWD, "knn_bwd": n_samples * BYTES_PER_SAMPLE_KNN_BWD}
+        info = {"workload": "knn_aggregation: 5000 rays x 48 samples (the mapping step's sample placement) against 1,048,576 neural "
+                            "points U(bound) with 32-ch features, K = 8 within radius %.2f m, fwd + bwd into the feature rows and "
+                            "the camera 7-vector; BUILDER-DEFINED SEMANTICS (no reference implementation exists, SURVEY 8c)" % KNN_RADIUS,
+                "rays_per_step_per_gpu": 5000, "samples_per_ray": S, "neural_points": n_pts,
+                "parallelism": f"ray-shard dp{world}" + (" + NCCL all-reduce of the (P,32) feature gradient" if world > 1 else "")}
+        after_step = lambda: None
+        graph_gens = [gen]
+        result_of = lambda out: out
     elif cfgname in ("dense", "mesh256"):
         P_, bound, model, grids, renderer = build_scene(dev, True)
         fh = synthetic_frames(1, 100)[0]
@@ -397,7 +464,7 @@ def run_ours(args):
 
     # ---------------------------------------------------------------- stepping machinery
     graph = {"g": None, "out": None, "launches": 0}
-    graphable = cfgname in ("mapping", "tracking", "imap") and not args.no_graph
+    graphable = cfgname in ("mapping", "tracking", "imap", "knn") and not args.no_graph
 
     def h2d_inputs():
         for dst, src in zip(dev_in, pinned):
@@ -568,10 +635,7 @@ def run_ours(args):
                     "kernel_share_of_step": {k: round(v, 3) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
                     "kernel_ms": {k: round(statistics.mean(v), 4) for k, v in sorted(kern.items(), key=lambda kv: -sum(kv[1]))},
                     "kernel_frac_of_hbm": {k: round(alg[k] / (statistics.mean(v) * 1e-3) / 1e9 / hbm, 3) for k, v in kern.items() if alg.get(k)},
-                    "note": "decoder layers run on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulate in TMEM); the decoder "
-                            "kernels are latency/issue-bound (tensor pipe 10-16% active, 16-24 warps/SM), not HBM-bound; the grids "
-                            "(46 MiB) are L2-resident, so DRAM traffic is far below the algorithmic bytes; HBM roofline is the "
-                            "BASELINE.md denominator"}
+                    "note": ROOFLINE_NOTE_KNN if cfgname == "knn" else ROOFLINE_NOTE}
     step_frac = (value / world * bytes_per_unit / (hbm * 1e9)) if bytes_per_unit else None
     h2d_bytes = sum(t.numel() * t.element_size() for t in pinned)
     line = {"metric": metric, "value": round(value, 1), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -584,7 +648,7 @@ def run_ours(args):
                            launch=("whole iteration captured once in a CUDA graph and replayed" if graph["g"] is not None else "eager launches"),
                            eager_ms_per_step=round(ms_eager / args.steps, 4)),
             "e2e": {"value": round(e2e_value, 1), "unit": unit, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 8 if cfgname in ("mapping", "tracking", "imap") else (H * W * 8 if cfgname == "dense" else 256 ** 3 * 4),
+                    "d2h_bytes_per_step": 8 if cfgname in ("mapping", "tracking", "imap", "knn") else (H * W * 8 if cfgname == "dense" else 256 ** 3 * 4),
                     "ms_per_step": round(ms_e2e / args.steps, 4),
                     "h2d": "next step's inputs prefetched on a copy stream while the current step computes; a step ends only after "
                            "its prefetch has landed" if graph["g"] is not None else "inputs copied from pinned memory at the start of each step",
@@ -606,6 +670,8 @@ def run_ours(args):
             line["torch_eager_cuda"] = torch_eager_cuda_baseline(dev)
         except Exception as exc:
             line["torch_eager_cuda"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    if rank == 0 and world == 1 and not args.light and cfgname == "knn":
+        line["cpu_baseline"] = knn_cpu()
     if rank == 0:
         emit(line)
     # Teardown.  A captured graph that contains NCCL kernels must be released before the process group
@@ -733,6 +799,29 @@ def cpu_baseline(budget_s=15.0, threads=None, pix=PIX_PER_KF):
             "sample": f"same mapping iteration (incl. Adam step) on {N_KEYFRAMES} x {pix} px = {rays} rays, torch CPU, best of {n} after 1 warm-up"}
 
 
+def knn_cpu_baseline(xyz, feat, p, gw, radius, rays=200, budget_s=12.0):
+    """k-NN aggregation fwd+bwd of the oracle port on the host cores: scipy cKDTree ball query (float64) + float32 re-ranking
+    + torch blend and autograd, on the first `rays` rays of the step's sample points (the tree build is not timed: our index
+    build is not part of the step either)."""
+    from scipy.spatial import cKDTree
+    from oracle import knn_oracle as KO
+    tree = cKDTree(xyz.double().numpy())
+    n = rays * S
+    pn, xn = p[:n].contiguous(), xyz.numpy()
+    best, reps, t_begin = float("inf"), 0, time.perf_counter()
+    while reps < 1 or (time.perf_counter() - t_begin < budget_s and reps < 10):
+        t0 = time.perf_counter()
+        idx, _ = KO.knn_query(pn.numpy(), xn, radius, tree)
+        pt = pn.clone().requires_grad_(True)
+        ft = feat.clone().requires_grad_(True)
+        (KO.aggregate(pt, xyz, ft, torch.from_numpy(idx), 1e-6) * gw[:n]).sum().backward()
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    return {"value": round(rays / best, 1), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port (cKDTree.query_ball_point + float32 re-ranking + torch blend, fwd+bwd) on {rays} rays x {S} samples "
+                      f"of the same batch against the same 1,048,576 points, best of {reps}"}
+
+
 def torch_eager_cuda_baseline(dev, steps=10):
     """The reference's op graph (oracle port, unmodified torch ops, allow_tf32 off) on the same GPU: the reference's real
     deployment is torch eager on CUDA, so this is the honest number to beat."""
@@ -816,7 +905,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="mapping", choices=["mapping", "tracking", "dense", "mesh256", "imap"])
+    ap.add_argument("--config", default="mapping", choices=["mapping", "tracking", "dense", "mesh256", "imap", "knn"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back replays for the sustained-clock figure (0: skip)")
     ap.add_argument("--no-optimizer", action="store_true", help="mapping: leave the Adam step out of the timed iteration")

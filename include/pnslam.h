@@ -385,6 +385,37 @@ int pn_sparse_rows_apply(float* dense, int64_t V, int nsrc, const uint32_t* cons
 /* out[i] = src_0[i] + src_1[i] + ... in source order (decoder / pose gradients riding in the same exchange). */
 int pn_dense_sum(float* out, int64_t n, int nsrc, const float* const* srcs, void* stream);
 
+/* -------- k-nearest neural-point feature aggregation (BASELINE.json config 4) --------
+ * BUILDER-DEFINED SEMANTICS, NOT REFERENCE PARITY: the reference has no 3-D neural-point aggregation;
+ * its nearest code is the 2-D cKDTree radius search of src/frame.py:362-366 / src/search_points.py:122,223,445.
+ * Specification: the K = 8 nearest neural points within `radius` of a sample point, weights
+ * w_k = 1 / (d_k^2 + eps), blended feature f = sum_k w_k F[i_k] / sum_k w_k (zero when no point lies within the radius).
+ * Distances are float32, d2 = ((dx*dx) + (dy*dy)) + (dz*dz) with individually rounded operations; neighbours are ordered
+ * by (d2, point index), so the index lists are deterministic and bit-exact against oracle/knn_oracle.py. */
+#define PN_KNN_K 8
+typedef struct pn_knn_index {
+  const int32_t* start; /* [nx*ny*nz + 1]: first slot of every cell in `sorted` (cell = (cz*ny + cy)*nx + cx) */
+  const float* sorted;  /* [P] float4 {x, y, z, bit pattern of the point's index}: the points grouped by cell */
+  float lo[3];          /* lower corner of the cell lattice */
+  float inv_h;          /* 1 / cell edge; cell coordinate = clamp(floor((x - lo) * inv_h), 0, n-1), float32 */
+  int nx, ny, nz;
+  int P;
+} pn_knn_index;
+/* Fill index->start and index->sorted from xyz (P,3) float32 (every point must lie inside the lattice: the caller's
+ * check).  scratch: int32[2*P + nx*ny*nz]. */
+int pn_knn_build(const float* xyz, int P, const pn_knn_index* index, int32_t* scratch, void* stream);
+/* idx (N,8) int32: original indices of the nearest points in ascending (d2, index) order, -1 where fewer than 8 lie
+ * within the radius; d2 (N,8) float32 (optional; 0 in the empty slots).  radius <= the index's cell edge. */
+int pn_knn_query(const pn_points* pts, const pn_knn_index* index, float radius, int32_t* idx, float* d2, void* stream);
+/* query + blend in one launch: also out (N,32) float32.  feat: [P][32] float32 rows. */
+int pn_knn_aggregate_fwd(const pn_points* pts, const pn_knn_index* index, float radius, float eps, const float* feat,
+                         int32_t* idx, float* d2, float* out, void* stream);
+/* VJP of the blend for g_out (N,32): g_feat [P][32] += (vector atomics; optional), g_pts (N,3) =/+= (optional;
+ * the neighbour SET is piecewise constant in p, so only the weights carry a point gradient). */
+int pn_knn_aggregate_bwd(const pn_points* pts, const int32_t* idx, const float* d2, float eps, const float* feat,
+                         const float* xyz, const float* g_out, float* g_feat, float* g_pts, int accumulate_pts,
+                         void* stream);
+
 /* -------- utilities -------- */
 /* (1,32,Z,Y,X) contiguous <-> channels-last [Z][Y][X][32]; `to_channels_last` = 1 or 0. */
 int pn_grid_transpose(const float* src, float* dst, int D, int H, int W, int to_channels_last, void* stream);

@@ -14,10 +14,11 @@ Modules
   dist      ray sharding + NCCL gradient all-reduce for the mapping step
   losses    mapping_loss / tracking_loss: the Mapper's and Tracker's loss heads with their gradients, one launch each
   graphs    GraphedStep: one tracking / mapping iteration captured in a CUDA graph
+  knn       NeuralPointField / NeuralPointIndex: k-nearest neural-point feature aggregation (BASELINE config 4; builder-defined semantics)
   csrc/     CUDA kernels (sm_100a) and the C ABI
 """
 
-from . import _lib, engine, common, decoder, config, renderer, graphs, losses, mapper  # noqa: E402,F401
+from . import _lib, engine, common, decoder, config, renderer, graphs, losses, mapper, knn  # noqa: E402,F401
 from .renderer import Renderer  # noqa: E402,F401
 from .decoder import NICE, MLP, MLP_no_xyz  # noqa: E402,F401
 from .config import get_model, load_bound, grid_init, attach_bounds  # noqa: E402,F401

@@ -318,8 +318,7 @@ extern "C" int pn_knn_build(const float* xyz, int P, const pn_knn_index* index, 
   const int64_t ncell = (int64_t)index->nx * index->ny * index->nz;
   if (ncell > (1ll << 30)) { set_error("pn_knn_build: %lld cells is more than the 2^30 the index supports", (long long)ncell); return 1; }
   int32_t* start = const_cast<int32_t*>(index->start);
-  // the counts are accumulated in start[1..] ... no: in scratch[2P ..) would need ncell more words; use start itself shifted?
-  // Simpler and explicit: scratch = cell_of [P] | rank [P] | counts [ncell]
+  // scratch = cell_of [P] | rank [P] | counts [ncell]
   int32_t* cell_of = scratch;
   int32_t* rank = scratch + P;
   int32_t* counts = scratch + 2 * (int64_t)P;
@@ -344,7 +343,7 @@ extern "C" int pn_knn_query(const pn_points* pts, const pn_knn_index* index, flo
   if (!idx) { set_error("pn_knn_query: null output"); return 1; }
   if (radius * index->inv_h > 1.0f) { set_error("pn_knn_query: radius %g exceeds the cell edge %g of the index", radius, 1.0 / index->inv_h); return 1; }
   k_knn_fwd<false><<<(unsigned)((pts->N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      *pts, make_cells(index), index->start, reinterpret_cast<const float4*>(index->sorted), __fmul_rn_host(radius), 0.f, nullptr, idx, d2, nullptr);
+      *pts, make_cells(index), index->start, reinterpret_cast<const float4*>(index->sorted), radius * radius, 0.f, nullptr, idx, d2, nullptr);
   return launch_status("k_knn_fwd");
 }
 
@@ -355,7 +354,7 @@ extern "C" int pn_knn_aggregate_fwd(const pn_points* pts, const pn_knn_index* in
   if (!idx || !d2 || !out || !feat) { set_error("pn_knn_aggregate_fwd: null pointer"); return 1; }
   if (radius * index->inv_h > 1.0f) { set_error("pn_knn_aggregate_fwd: radius %g exceeds the cell edge %g of the index", radius, 1.0 / index->inv_h); return 1; }
   k_knn_fwd<true><<<(unsigned)((pts->N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      *pts, make_cells(index), index->start, reinterpret_cast<const float4*>(index->sorted), __fmul_rn_host(radius), eps, feat, idx, d2, out);
+      *pts, make_cells(index), index->start, reinterpret_cast<const float4*>(index->sorted), radius * radius, eps, feat, idx, d2, out);
   return launch_status("k_knn_fwd");
 }
 

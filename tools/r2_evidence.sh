@@ -8,7 +8,7 @@ set -x
 if [[ -z "${SKIP_TESTS:-}" ]]; then timeout 900 python -m pytest tests -m gpu -q > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log; tail -3 $O/tests.log; fi
 timeout 300 python bench.py > $O/bench_mapping.json 2> $O/bench_mapping.err; echo "rc=$?"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err; echo "rc=$?"
-for c in tracking dense mesh256 imap; do
+for c in tracking dense mesh256 imap knn; do
   timeout 300 python bench.py --config $c > $O/bench_$c.json 2> $O/bench_$c.err; echo "$c rc=$?"
 done
 if [[ -z "${SKIP_NCU:-}" ]]; then
