@@ -80,7 +80,9 @@ constexpr uint32_t O_WE = 0;                         // [W0; W3[:, :93]] as one 
 constexpr uint32_t O_WH = O_WE + 4 * bbytes(96);     // 4 x [32 x 32]: hi, lo per block
 template <int CD> __host__ __device__ constexpr uint32_t o_wc() { return O_WH + 4 * 2 * bbytes(32); }   // [160 x CD]: hi, then lo
 template <int CD> __host__ __device__ constexpr uint32_t o_a() { return o_wc<CD>() + 5u * 2u * bbytes(CD); }   // A buffers
-template <int CD> __host__ __device__ constexpr uint32_t o_small() { return o_a<CD>() + 2u * 2u * kABytes; }
+// forward kernels: K-stride of the A operand's core matrices (padded where shared memory allows: no store bank conflicts)
+template <int CD> __host__ __device__ constexpr uint32_t a_lbo() { return CD == 32 ? 144u : 128u; }
+template <int CD> __host__ __device__ constexpr uint32_t o_small() { return o_a<CD>() + 2u * 2u * 16u * 8u * a_lbo<CD>(); }
 constexpr int S_B = 0, S_BIAS = 288, S_BC = 448, S_WO = 608, S_BO = 736, S_TOTAL = 740;  // floats
 // the two mbarriers and the TMEM base address follow the float area (kept in dynamic shared
 // memory: with c_dim 64 the kernel uses all but ~100 bytes of the 227 KB an SM offers)
@@ -90,8 +92,10 @@ template <int CD> __host__ __device__ constexpr uint32_t smem_total() { return o
 // columns, zero beyond) into canonical hi / lo operands
 __device__ __forceinline__ void stage_b(unsigned char* hi, unsigned char* lo, const float* __restrict__ src, int ld, int col0, int K,
                                         int kvalid) {
+  // lane bits = (k & 3, n & 7): a warp's 32 stores fill one 128-byte core matrix (no bank conflicts)
   for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
-    const int n = i / K, k = i - n * K;
+    const int rest = i >> 5, kc = rest % (K / 4), ng = rest / (K / 4);
+    const int n = ng * 8 + ((i >> 2) & 7), k = kc * 4 + (i & 3);
     const float w = k < kvalid ? src[n * ld + col0 + k] : 0.f;
     float h, l;
     umma::split_tf32(w, h, l);

@@ -13,6 +13,12 @@ template <int CD, int NOUT, bool BITS>
 __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using namespace tc;
+  // A operand: core matrices adjacent in K are kALbo bytes apart.  144 instead of 128 puts the eight 16-byte stores of a
+  // quarter-warp in put_rows (one sample row, channel quads 0..7) into eight different bank groups; with 128 they were
+  // 8-way bank conflicts = 21 % (c_dim 32) to 44 % (c_dim 64) of the kernel's shared-memory wavefronts, and the
+  // shared-memory data pipe (operand reads of the tensor core + these stores) is what bounds the forward kernels.
+  // c_dim 64 has no room for the padding (8 KB): it keeps 128.
+  constexpr uint32_t kALbo = a_lbo<CD>(), kASbo = 8u * kALbo, kABytes = 16u * kASbo;
   const int tid = threadIdx.x, lane = tid & 31;
   const int grp = tid >> 8, gw = (tid >> 5) & 7, quarter = gw & 3, half = gw >> 2;
   const int row = quarter * 32 + lane, col0 = 16 * half;
@@ -52,14 +58,14 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   uint64_t* bar = &bars[grp];
   uint32_t phase = 0;
   const bool issuer = (tid & 255) == 0;
-  const uint64_t dA_hi = umma::smem_desc(sA, kLbo, kASbo), dA_lo = umma::smem_desc(sAlo, kLbo, kASbo);
-  constexpr uint32_t kStep = (2u * kLbo) >> 4;   // one K-step of 8 in descriptor address units
+  const uint64_t dA_hi = umma::smem_desc(sA, kALbo, kASbo), dA_lo = umma::smem_desc(sAlo, kALbo, kASbo);
+  constexpr uint32_t kStep = (2u * kLbo) >> 4, kAStep = (2u * kALbo) >> 4;   // one K-step of 8 in descriptor address units
   // D[:, dcol .. dcol+N) (+)= A . B[:, 32*k32 .. 32*k32+31]^T for the [N x Kb] operand whose hi copy
   // starts at byte offset boff and whose lo copy follows lo_off bytes later
   auto mma = [&](uint32_t dcol, uint32_t boff, uint32_t lo_off, int Kb, int k32, uint32_t idesc, uint32_t acc) {
     const uint32_t bh = sW + boff + (uint32_t)k32 * 8u * kLbo;
     const uint64_t dB_hi = umma::smem_desc(bh, kLbo, bsbo(Kb)), dB_lo = umma::smem_desc(bh + lo_off, kLbo, bsbo(Kb));
-    umma::mma_3xtf32_k32(tm + dcol, dA_hi, dA_lo, dB_hi, dB_lo, kStep, kStep, idesc, acc);
+    umma::mma_3xtf32_k32(tm + dcol, dA_hi, dA_lo, dB_hi, dB_lo, kAStep, kStep, idesc, acc);
   };
   // A written by every thread of the group -> one thread issues the MMAs and commits them to the barrier
   auto publish_issue = [&](auto&& issue) {
@@ -77,55 +83,87 @@ __global__ void __launch_bounds__(512, 1) k_grid_mlp_fwd_tc(const FwdArgs a) {
   };
   // this thread's 16 columns of its row -> A operand (hi and lo)
   auto store_half_row = [&](const float (&v)[16]) {
-    const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)(4 * half) * kLbo;
+    const uint32_t base = (uint32_t)(row >> 3) * kASbo + (uint32_t)(row & 7) * 16u + (uint32_t)(4 * half) * kALbo;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float4 h, l;
       umma::split_tf32(v[4 * q], h.x, l.x); umma::split_tf32(v[4 * q + 1], h.y, l.y);
       umma::split_tf32(v[4 * q + 2], h.z, l.z); umma::split_tf32(v[4 * q + 3], h.w, l.w);
-      *reinterpret_cast<float4*>(a_hi + base + q * kLbo) = h;
-      *reinterpret_cast<float4*>(a_lo + base + q * kLbo) = l;
+      *reinterpret_cast<float4*>(a_hi + base + q * kALbo) = h;
+      *reinterpret_cast<float4*>(a_lo + base + q * kALbo) = l;
     }
   };
-  // trilinear features of rows 32*quarter + 16*half + [0,16): 8 lanes per sample (lane&7 = channel quad,
-  // 128-bit loads), 4 samples per iteration; the values stay in registers until put_rows
+  // trilinear features of rows 32*quarter + 16*half + [0,16), gathered with 128-bit loads into registers (gather16) and
+  // stored as the A operand later (put_rows).  Two lane mappings, both free of shared-memory bank conflicts:
+  //   c_dim 32: 8 lanes per sample (lane & 7 = channel quad: one 128-byte voxel row per corner), 4 samples per iteration;
+  //             the quarter-warp's stores (one row, quads 0..7) are kALbo = 144 bytes apart -> eight different bank groups;
+  //   c_dim 64: no room for the padding, so the SAMPLE sits in the low lane bits (s = lane & 7) and a lane loads quads
+  //             lane >> 3 and (lane >> 3) + 4 of its sample, 8 samples per iteration: a quarter-warp stores eight
+  //             consecutive rows of one core matrix = 128 contiguous bytes.  (Costs L1 tag lookups -- 8 lines per load
+  //             instruction instead of 4 -- which is why c_dim 32 prefers the padding.)
   auto gather16 = [&](const GridDev& g, float ux, float uy, float uz, unsigned vm, float* __restrict__ Cst, int64_t N, int64_t nq,
                       float4 (&out)[4]) {
-    const int q = lane & 7, sub = lane >> 3;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int src = 16 * half + 4 * it + sub;   // lane (within this warp) that owns the row
-      const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
+    auto corners = [&](const Cell& c, int q) {
+      const float4* gp = reinterpret_cast<const float4*>(g.data + c.base) + q;
+      float4 val[8];
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((vm >> src) & 1u) {
-        const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
-        const float4* gp = reinterpret_cast<const float4*>(g.data + c.base) + q;
-        float4 val[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          val[k] = ((c.ok >> k) & 1u) ? __ldg(gp + corner_offset(k, g.W, g.H) / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 8; ++k)
+        val[k] = ((c.ok >> k) & 1u) ? __ldg(gp + corner_offset(k, g.W, g.H) / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if ((c.ok >> k) & 1u) {
-            const float w = corner_weight(c, k);
-            v.x = __fadd_rn(v.x, __fmul_rn(val[k].x, w)); v.y = __fadd_rn(v.y, __fmul_rn(val[k].y, w));
-            v.z = __fadd_rn(v.z, __fmul_rn(val[k].z, w)); v.w = __fadd_rn(v.w, __fmul_rn(val[k].w, w));
+      for (int k = 0; k < 8; ++k) {
+        if ((c.ok >> k) & 1u) {
+          const float w = corner_weight(c, k);
+          v.x = __fadd_rn(v.x, __fmul_rn(val[k].x, w)); v.y = __fadd_rn(v.y, __fmul_rn(val[k].y, w));
+          v.z = __fadd_rn(v.z, __fmul_rn(val[k].z, w)); v.w = __fadd_rn(v.w, __fmul_rn(val[k].w, w));
+        }
+      }
+      return v;
+    };
+    if constexpr (CD == 32) {
+      const int q = lane & 7, sub = lane >> 3;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int src = 16 * half + 4 * it + sub;   // lane (within this warp) that owns the row
+        const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((vm >> src) & 1u) {
+          v = corners(make_cell(sx, sy, sz, g.W, g.H, g.D), q);
+          if (Cst) reinterpret_cast<float4*>(Cst)[(int64_t)q * N + nq + src] = v;
+        }
+        out[it] = v;
+      }
+    } else {
+      const int s = lane & 7, qh = lane >> 3;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int src = 16 * half + 8 * it + s;
+        const float sx = __shfl_sync(kFull, ux, src), sy = __shfl_sync(kFull, uy, src), sz = __shfl_sync(kFull, uz, src);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if ((vm >> src) & 1u) {
+          const Cell c = make_cell(sx, sy, sz, g.W, g.H, g.D);
+          v0 = corners(c, qh);
+          v1 = corners(c, qh + 4);
+          if (Cst) {
+            reinterpret_cast<float4*>(Cst)[(int64_t)qh * N + nq + src] = v0;
+            reinterpret_cast<float4*>(Cst)[(int64_t)(qh + 4) * N + nq + src] = v1;
           }
         }
-        if (Cst) reinterpret_cast<float4*>(Cst)[(int64_t)q * N + nq + src] = v;
+        out[2 * it] = v0;
+        out[2 * it + 1] = v1;
       }
-      out[it] = v;
     }
   };
   auto put_rows = [&](const float4 (&v)[4]) {
-    const int q = lane & 7, sub = lane >> 3;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = quarter * 32 + 16 * half + 4 * it + sub;
+    for (int j = 0; j < 4; ++j) {
+      int r, q;
+      if constexpr (CD == 32) { q = lane & 7; r = quarter * 32 + 16 * half + 4 * j + (lane >> 3); }
+      else { q = (lane >> 3) + 4 * (j & 1); r = quarter * 32 + 16 * half + 8 * (j >> 1) + (lane & 7); }
       float4 h, l;
-      umma::split_tf32(v[it].x, h.x, l.x); umma::split_tf32(v[it].y, h.y, l.y);
-      umma::split_tf32(v[it].z, h.z, l.z); umma::split_tf32(v[it].w, h.w, l.w);
-      const uint32_t off = (uint32_t)(r >> 3) * kASbo + (uint32_t)(r & 7) * 16u + (uint32_t)q * kLbo;
+      umma::split_tf32(v[j].x, h.x, l.x); umma::split_tf32(v[j].y, h.y, l.y);
+      umma::split_tf32(v[j].z, h.z, l.z); umma::split_tf32(v[j].w, h.w, l.w);
+      const uint32_t off = (uint32_t)(r >> 3) * kASbo + (uint32_t)(r & 7) * 16u + (uint32_t)q * kALbo;
       *reinterpret_cast<float4*>(a_hi + off) = h;
       *reinterpret_cast<float4*>(a_lo + off) = l;
     }

@@ -344,17 +344,25 @@ def plan_forward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, dev
 
     # The colour pass (SET_RGB) and the occupancy passes write disjoint components of raw, so with PARALLEL_FORWARD the
     # colour pass goes to a side stream (the two chains could fill each other's tails; see the flag for what was measured).
-    side = _side_stream(device) if (PARALLEL_FORWARD and any(p.out_mode == L.OUT_SET_RGB for p in plan.passes)) else None
+    side = _side_stream(device) if (PARALLEL_FORWARD and len(plan.passes) > 1 and
+                                    any(p.out_mode == L.OUT_SET_RGB for p in plan.passes)) else None
     with L.device_guard(device):
         main = torch.cuda.current_stream(device)
         if side is not None:
             side.wait_stream(main)
+        # SM_SPLIT: the two chains get disjoint shares of the SMs (persistent kernels, one CTA per SM), so they really run
+        # side by side instead of one filling the other's tail
+        cost = [_FWD_COST.get(p.dec.name if p.kind == "grid" else p.kind, 1.0) for p in plan.passes]
+        on_side = [side is not None and p.out_mode == L.OUT_SET_RGB for p in plan.passes]
+        share = _sm_shares(sum(c for c, s_ in zip(cost, on_side) if s_), sum(c for c, s_ in zip(cost, on_side) if not s_)) \
+            if (side is not None and SM_SPLIT) else None
         for i, p in enumerate(plan.passes):
-            if side is not None and p.out_mode == L.OUT_SET_RGB:
-                with torch.cuda.stream(side):
+            if on_side[i]:
+                with torch.cuda.stream(side), _sm_budget(share[0] if share else None):
                     run_pass(i, p)
             else:
-                run_pass(i, p)
+                with _sm_budget(share[1] if share else None):
+                    run_pass(i, p)
         if side is not None:
             main.wait_stream(side)
     return raw, stashes
@@ -452,12 +460,37 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
         main = torch.cuda.current_stream(device)
         if side is not None:
             side.wait_stream(main)
+        cost = [_BWD_COST.get(p.dec.name if p.kind == "grid" else p.kind, 1.0) + (_WGRAD_COST if want_w[i] else 0.0)
+                for i, p in enumerate(plan.passes)]
+        n_chains = BWD_STREAMS if BWD_STREAMS > 0 else (2 if any(want_w) else 3)
+        three = side is not None and SM_SPLIT and n_chains >= 3 and len(plan.passes) == 3
+        if three:      # one chain per pass, SMs in proportion to the passes' costs
+            side2 = _side_stream(device, 1)
+            side2.wait_stream(main)
+            total = sum(_sm_shares(1.0, 1.0))
+            a = max(1, int(round(total * cost[1] / sum(cost))))
+            b = max(1, int(round(total * cost[2] / sum(cost))))
+            budgets, streams = [total - a - b, a, b], [None, side, side2]
+            for i, p in enumerate(plan.passes):
+                if streams[i] is None:
+                    with _sm_budget(budgets[i]):
+                        run_pass(i, p)
+                else:
+                    with torch.cuda.stream(streams[i]), _sm_budget(budgets[i]):
+                        run_pass(i, p)
+            main.wait_stream(side)
+            main.wait_stream(side2)
+            return g_grids, g_pts, g_params
+        share = _sm_shares(sum(cost[1:]), cost[0]) if (side is not None and SM_SPLIT) else None
+        if share is not None and SM_SPLIT_BIAS:
+            share = (share[0] + SM_SPLIT_BIAS, share[1] - SM_SPLIT_BIAS)
         for i, p in enumerate(plan.passes):
             if side is not None and i >= 1:
-                with torch.cuda.stream(side):
+                with torch.cuda.stream(side), _sm_budget(share[0] if share else None):
                     run_pass(i, p)
             else:
-                run_pass(i, p)
+                with _sm_budget(share[1] if share else None):
+                    run_pass(i, p)
         if side is not None:
             main.wait_stream(side)
     return g_grids, g_pts, g_params
@@ -467,15 +500,59 @@ PARALLEL_BACKWARD = _os.environ.get("PN_PARALLEL_BACKWARD", "1") != "0"   # two-
 # colour pass beside the occupancy passes: possible (disjoint components of raw) but measured without gain on a B200
 # (mapping 1.25 ms, tracking 0.31 ms either way; +0.1 ms of host time in eager mode), so off by default
 PARALLEL_FORWARD = _os.environ.get("PN_PARALLEL_FORWARD", "0") != "0"
-_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+# With two chains in flight, give each a fixed share of the SMs in proportion to its measured cost (B200, 240,000 samples:
+# forward colour 0.157 / fine 0.184 / middle 0.139 ms; backward colour 0.19 (+ weight gradients 0.15) / fine 0.16 / middle 0.20)
+#
+# Measured on a B200 (graph replay, L2 flushed): mapping iteration 1.22-1.23 ms with two full-grid chains (the second chain's
+# CTAs only fill the first's tail) -> 1.16-1.17 ms with the SMs split 76 / 72 between [colour backward + weight gradients] and
+# [fine + middle backward]; +-4 SMs off that balance costs 1-3 %.  Tracking (no weight gradients, 375 tiles per kernel = less
+# than one wave): one chain per pass on a third of the SMs each, 0.309 -> 0.295 ms.  The forward chains gain nothing from a split
+# (colour beside fine -> middle: 1.19 ms against 1.17-1.19 with the backward split alone), so PARALLEL_FORWARD stays off.
+SM_SPLIT = _os.environ.get("PN_SM_SPLIT", "1") != "0"
+SM_SPLIT_BIAS = int(_os.environ.get("PN_SM_SPLIT_BIAS", "0"))     # SMs moved from the main chain to the side chain (tuning)
+BWD_STREAMS = int(_os.environ.get("PN_BWD_STREAMS", "0"))         # 0: three chains when no pass computes weight gradients, else two
+_FWD_COST = {"color": 0.157, "fine": 0.184, "middle": 0.139, "coarse": 0.05}
+_BWD_COST = {"color": 0.19, "fine": 0.16, "middle": 0.20, "coarse": 0.05}
+_WGRAD_COST = float(_os.environ.get("PN_WGRAD_COST", "0.19"))   # 0.15 ms alone; 0.19 balances the chains when they run side by side
+_SIDE_STREAMS: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
 
 
-def _side_stream(device) -> "torch.cuda.Stream":
+def _sm_shares(cost_side: float, cost_main: float) -> Tuple[int, int]:
+    """(SMs for the side chain, SMs for the main chain) out of what pn_reserve_sms currently leaves."""
+    lib = L.lib()
+    reserved = lib.pn_reserve_sms(0)
+    lib.pn_reserve_sms(reserved)
+    total = max(2, torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count - reserved)
+    a = min(total - 1, max(1, int(round(total * cost_side / max(cost_side + cost_main, 1e-9)))))
+    return a, total - a
+
+
+class _sm_budget:
+    """``with _sm_budget(n):`` the persistent kernels launched inside size their grids for n SMs (None: unchanged)."""
+
+    def __init__(self, n: Optional[int]):
+        self.n = n
+
+    def __enter__(self):
+        if self.n is not None:
+            lib = L.lib()
+            full = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            self.prev = lib.pn_reserve_sms(max(0, full - self.n))
+        return self
+
+    def __exit__(self, *exc):
+        if self.n is not None:
+            L.lib().pn_reserve_sms(self.prev)
+        return False
+
+
+def _side_stream(device, which: int = 0) -> "torch.cuda.Stream":
     idx = torch.device(device).index
     idx = torch.cuda.current_device() if idx is None else idx
-    if idx not in _SIDE_STREAMS:
-        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
-    return _SIDE_STREAMS[idx]
+    key = (idx, which)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx)
+    return _SIDE_STREAMS[key]
 
 
 # Optional callback ``hook(key, grad)`` fired from inside the backward as soon as a gradient
