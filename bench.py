@@ -83,9 +83,10 @@ KNN_RADIUS = 0.16
 METRIC = "rays/sec fwd+bwd render_batch_ray (NICE mapping iteration, stage color)"
 
 
-ROOFLINE_NOTE = ("decoder layers run on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulate in TMEM); the decoder kernels are "
-                 "latency/issue-bound (tensor pipe 10-16% active, 16-24 warps/SM), not HBM-bound; the grids (46 MiB) are L2-resident, "
-                 "so DRAM traffic is far below the algorithmic bytes; HBM roofline is the BASELINE.md denominator")
+ROOFLINE_NOTE = ("decoder layers run on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulate in TMEM); the decoder kernels are bound by "
+                 "the shared-memory data pipe (tensor-core operand reads + operand stores: 0.5-0.6 wavefronts per cycle, 0.96 in the "
+                 "weight-gradient kernel) and by the latency of the 5-9 dependent MMA round trips per tile, not by HBM; the grids "
+                 "(46 MiB) are L2-resident, so DRAM traffic is far below the algorithmic bytes; HBM roofline is the BASELINE.md denominator")
 ROOFLINE_NOTE_KNN = ("integer/float32 search + gather: no GEMM, SIMT kernels only; the candidate scan of the 27 neighbouring cells "
                      "(~150 position records per sample, L1/L2 hits) is not part of the algorithmic bytes")
 
