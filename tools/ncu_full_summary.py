@@ -14,7 +14,9 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "lts__t_sectors_op_red.sum",
            "lts__t_sectors_op_atom.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
-           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
+           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sm__cycles_active.avg", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum"]
 UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
 
 
