@@ -47,6 +47,41 @@ class _MappingLossFn(torch.autograd.Function):
         return gd, gc, None, None, None, None, None
 
 
+def mapping_loss_and_grads(depth: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
+                           gt_color: Optional[torch.Tensor], stage: str = "color", w_color: float = 0.2, nice: bool = True,
+                           depth_supervision: bool = True):
+    """The same launch as ``mapping_loss`` without an autograd node: (loss, d loss / d depth (R,) in depth's dtype,
+    d loss / d colour (R,3) or None).  A caller that owns the whole iteration (``mapping.MappingIteration``) seeds the
+    renderer's backward with these directly -- ``torch.autograd.backward([depth, color], [g_depth, g_color])`` -- which
+    saves the three launches autograd spends on the loss node (a ones() fill and two scalings by it)."""
+    if not depth.is_cuda:
+        raise RuntimeError("pointnerf_slam_b200.losses.mapping_loss_and_grads needs CUDA tensors (there is no CPU path)")
+    use_color = ((not nice) or stage == "color") and color is not None and gt_color is not None
+    if not depth_supervision and not use_color:
+        raise ValueError("mapping_loss: without depth supervision the loss is the colour term (stage 'color' or iMAP*)")
+    dev = depth.device
+    d = depth.detach().double().contiguous()
+    gd = gt_depth.detach().float().contiguous()
+    R = d.shape[0]
+    loss = torch.empty((), dtype=torch.float64, device=dev)
+    g_depth = torch.empty(R, dtype=torch.float64, device=dev)
+    c = gc = g_color = None
+    if use_color:
+        c = color.detach().float().contiguous()
+        gc = gt_color.detach().float().contiguous()
+        g_color = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    with L.device_guard(dev):
+        L.check(L.lib().pn_mapping_loss(C.c_void_p(d.data_ptr()), C.c_void_p(L.ptr(c)), C.c_void_p(gd.data_ptr()),
+                                        C.c_void_p(L.ptr(gc)), C.c_int64(R), int(use_color), C.c_float(w_color),
+                                        int(bool(depth_supervision)), C.c_void_p(loss.data_ptr()), C.c_void_p(g_depth.data_ptr()),
+                                        C.c_void_p(L.ptr(g_color)), C.c_void_p(L.stream_ptr(dev))), "pn_mapping_loss")
+    if g_depth.dtype != depth.dtype:
+        g_depth = g_depth.to(depth.dtype)
+    if g_color is not None and g_color.dtype != color.dtype:
+        g_color = g_color.to(color.dtype)
+    return loss, g_depth, g_color
+
+
 def mapping_loss(depth: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
                  gt_color: Optional[torch.Tensor], stage: str = "color", w_color: float = 0.2, nice: bool = True,
                  depth_supervision: bool = True) -> torch.Tensor:

@@ -22,7 +22,7 @@ import torch
 from . import dist as D
 from . import engine as E
 from .common import KeyframeBatch, get_camera_from_tensor, get_samples_multi
-from .losses import mapping_loss
+from .losses import mapping_loss, mapping_loss_and_grads
 
 TRAINED_GRIDS = {"coarse": ("grid_coarse",), "middle": ("grid_middle",), "fine": ("grid_middle", "grid_fine"),
                  "color": ("grid_middle", "grid_fine", "grid_color")}
@@ -65,6 +65,7 @@ class MappingIteration:
             self._reducer = D.OverlappedGradReducer(arena if exchange == "arena" else None)
         self.last_indices = None
         self._batch: Optional[KeyframeBatch] = None
+        self._arena_join = None
 
     # ------------------------------------------------------------------------------------------
     def trained(self) -> List[torch.Tensor]:
@@ -88,14 +89,34 @@ class MappingIteration:
         c2w = get_camera_from_tensor(torch.stack(self.cams))
         return get_samples_multi(0, H, 0, W, self.n, H, W, fx, fy, cx, cy, c2w, self._batch, self.device, indices=idx)
 
-    def forward_loss(self, indices=None):
+    def _render(self, indices=None):
         ro, rd, gd, gc = self.sample(indices)
         self.renderer.depth_max_override = D.share_depth_max(gd) if self.world > 1 else None
         try:
             depth, var, color = self.renderer.render_batch_ray(self.grids, self.decoders, rd, ro, self.device, self.stage, gt_depth=gd)
         finally:
             self.renderer.depth_max_override = None
+        return depth, color, gd, gc
+
+    def forward_loss(self, indices=None):
+        """The iteration's loss as a differentiable scalar (``loss.backward()`` works as in the reference)."""
+        depth, color, gd, gc = self._render(indices)
         return mapping_loss(depth, color, gd, gc, self.stage, self.w_color)
+
+    def _backward(self, indices=None) -> torch.Tensor:
+        """Forward, loss and backward.  The loss kernel hands back d loss / d depth and d loss / d colour, and the renderer's
+        backward is seeded with them directly (no autograd node for the loss: three launches fewer per iteration)."""
+        depth, color, gd, gc = self._render(indices)
+        loss, g_depth, g_color = mapping_loss_and_grads(depth, color, gd, gc, self.stage, self.w_color)
+        outs, grads = [depth], [g_depth]
+        if g_color is not None:
+            outs.append(color)
+            grads.append(g_color)
+        if self._arena_join is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._arena_join)
+            self._arena_join = None
+        torch.autograd.backward(outs, grads)
+        return loss
 
     @staticmethod
     def _contiguous_block(tensors, numels):
@@ -156,16 +177,24 @@ class MappingIteration:
     def __call__(self, indices=None) -> torch.Tensor:
         if self.arena is not None:
             E.GRAD_ARENA = self.arena
-            self.arena.reset()
+            if self.arena.offset:
+                # the 46 MiB memset of the gradient sinks runs beside the forward (which takes nothing from the arena) on a
+                # side stream and is joined right before the backward
+                main, side = torch.cuda.current_stream(self.device), E._side_stream(self.device, 2)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self.arena.reset()
+                self._arena_join = side
+            else:
+                self.arena.reset()
         try:
-            loss = self.forward_loss(indices)
             if self._reducer is not None and self.world > 1:
                 with self._reducer:
-                    loss.backward()
+                    loss = self._backward(indices)
                 self._reducer.finish({k: self.grids[k] for k in self.grid_keys}, decoders=dict(self.dec_modules),
                                      others=[c.grad for c in self.shared_cams])
             else:
-                loss.backward()
+                loss = self._backward(indices)
                 if self._use_sparse:
                     self._exchange_sparse()
                 elif self.world > 1 and self.exchange == "dense":
