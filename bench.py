@@ -319,15 +319,17 @@ def run_ours(args):
         gen = torch.Generator(device=dev).manual_seed(77 + rank)
         Hc, Wc = H - 200, W - 200
 
+        from pointnerf_slam_b200.mapper import StageOptimizer
+        from pointnerf_slam_b200.tracking import TrackingIteration
+        cam0 = cam.detach().clone()
+        opt = StageOptimizer({}, [], [cam])
+        opt.set_lrs([0.0, 0.0, 0.0, 0.0, 0.0, 0.001])          # tracking cam_lr, configs/Replica/replica.yaml
+        track = TrackingIteration(renderer, model, grids, depth, color, cam, H, W, FX, FY, CX, CY, 1000, 100, 100, 0.5, True, True,
+                                  generator=gen, optimizer=opt)
+
         def step_body():
-            c = P.get_camera_from_tensor(cam)
-            idx = torch.randint(Hc * Wc, (1000,), device=dev, generator=gen)
-            o, d, gd, gc = P.get_samples(100, H - 100, 100, W - 100, 1000, H, W, FX, FY, CX, CY, c, depth, color, dev, indices=idx)
-            dd, vv, cc = renderer.render_batch_ray(grids, model, d, o, dev, "color", gt_depth=gd)
-            loss = P.losses.tracking_loss(dd, vv, cc, gd, gc, 0.5, True, True)
-            cam.grad = None
-            loss.backward()
-            return loss
+            cam.data.copy_(cam0)       # every timed iteration starts from the same pose (thousands of replays would drift off the scene)
+            return track()
         pinned = [fh[0].pin_memory(), fh[1].pin_memory()]
         dev_in = [depth, color]
         units_rank, unit, bytes_per_unit = 1000, "rays/s", BYTES_PER_RAY_TRACK
@@ -336,7 +338,8 @@ def run_ours(args):
         alg = {f"grid_mlp_fwd:{k}": n_samples * (2048 if k == "fine" else 1024) for k in ("color", "fine", "middle")}
         alg.update({f"grid_mlp_bwd:{k}": n_samples * (2048 if k == "fine" else 1024) for k in ("color", "fine", "middle")})
         info = {"workload": "nice_tracking_iter: 1000 px of the 480x1000 crop, 48 samples/ray, fwd+bwd to the camera 7-vector, "
-                            "fused tracker loss (handle_dynamic); replicas only (N ranks = N independent trackers)",
+                            "fused tracker loss (handle_dynamic), Adam step on the camera; replicas only (N ranks = N independent trackers)",
+                "optimizer_in_step": True,
                 "rays_per_step_per_gpu": 1000, "samples_per_ray": S, "parallelism": f"replicas x{world}"}
         after_step = lambda: None
         graph_gens = [gen]

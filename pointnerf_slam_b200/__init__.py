@@ -13,12 +13,14 @@ Modules
   config    get_model / load_bound / grid_init  (src/config.py, src/NICE_SLAM.py)
   dist      ray sharding + NCCL gradient all-reduce for the mapping step
   losses    mapping_loss / tracking_loss: the Mapper's and Tracker's loss heads with their gradients, one launch each
+  mapping   MappingIteration: one iteration of the Mapper's hot loop (sample, render, loss, backward, exchange, Adam step)
+  tracking  TrackingIteration: one iteration of the Tracker's pose optimisation
   graphs    GraphedStep: one tracking / mapping iteration captured in a CUDA graph
   knn       NeuralPointField / NeuralPointIndex: k-nearest neural-point feature aggregation (BASELINE config 4; builder-defined semantics)
   csrc/     CUDA kernels (sm_100a) and the C ABI
 """
 
-from . import _lib, engine, common, decoder, config, renderer, graphs, losses, mapper, knn  # noqa: E402,F401
+from . import _lib, engine, common, decoder, config, renderer, graphs, losses, mapper, knn, mapping, tracking  # noqa: E402,F401
 from .renderer import Renderer  # noqa: E402,F401
 from .decoder import NICE, MLP, MLP_no_xyz  # noqa: E402,F401
 from .config import get_model, load_bound, grid_init, attach_bounds  # noqa: E402,F401

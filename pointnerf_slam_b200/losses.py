@@ -132,6 +132,43 @@ class _TrackingLossFn(torch.autograd.Function):
 
 
 
+def tracking_loss_and_grads(depth: torch.Tensor, uncertainty: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
+                            gt_color: Optional[torch.Tensor], w_color: float = 0.5, use_color: bool = True,
+                            handle_dynamic: bool = True, depth_supervision: bool = True):
+    """The same launch as ``tracking_loss`` without an autograd node: (loss, d loss / d depth, d loss / d colour or None),
+    for a caller that seeds the renderer's backward itself (``tracking.TrackingIteration``)."""
+    if not depth.is_cuda:
+        raise RuntimeError("pointnerf_slam_b200.losses.tracking_loss_and_grads needs CUDA tensors (there is no CPU path)")
+    if depth.shape[0] == 0:
+        raise ValueError("tracking_loss needs at least one ray")
+    use_color = bool(use_color) and color is not None and gt_color is not None
+    if not depth_supervision and not use_color:
+        raise ValueError("tracking_loss: without depth supervision the loss is the colour term (use_color_in_tracking)")
+    dev = depth.device
+    d = depth.detach().double().contiguous()
+    v = uncertainty.detach().double().contiguous()
+    gd = gt_depth.detach().float().contiguous()
+    R = d.shape[0]
+    loss = torch.empty((), dtype=torch.float64, device=dev)
+    g_depth = torch.empty(R, dtype=torch.float64, device=dev)
+    c = gc = g_color = None
+    if use_color:
+        c = color.detach().float().contiguous()
+        gc = gt_color.detach().float().contiguous()
+        g_color = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    with L.device_guard(dev):
+        L.check(L.lib().pn_tracking_loss(C.c_void_p(d.data_ptr()), C.c_void_p(v.data_ptr()), C.c_void_p(L.ptr(c)),
+                                         C.c_void_p(gd.data_ptr()), C.c_void_p(L.ptr(gc)), C.c_int64(R), int(bool(handle_dynamic)),
+                                         int(use_color), C.c_float(w_color), int(bool(depth_supervision)), C.c_void_p(loss.data_ptr()),
+                                         C.c_void_p(g_depth.data_ptr()), C.c_void_p(L.ptr(g_color)),
+                                         C.c_void_p(L.stream_ptr(dev))), "pn_tracking_loss")
+    if g_depth.dtype != depth.dtype:
+        g_depth = g_depth.to(depth.dtype)
+    if g_color is not None and g_color.dtype != color.dtype:
+        g_color = g_color.to(color.dtype)
+    return loss, g_depth, g_color
+
+
 def tracking_loss(depth: torch.Tensor, uncertainty: torch.Tensor, color: Optional[torch.Tensor], gt_depth: torch.Tensor,
                   gt_color: Optional[torch.Tensor], w_color: float = 0.5, use_color: bool = True,
                   handle_dynamic: bool = True, depth_supervision: bool = True) -> torch.Tensor:
