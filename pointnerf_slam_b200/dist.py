@@ -354,6 +354,55 @@ class SparseGradExchange:
             if self.world > 1 and self.mode == "p2p":
                 self.handle.barrier(channel=1)                    # nobody overwrites a buffer a peer still reads
 
+    # -- the same exchange in two parts (allgather mode), for a caller that overlaps the first with other work ----------
+    def exchange_grids(self, grid_grads) -> None:
+        """Pack, all-gather and apply the touched rows of the grid gradients only (the tail section of the buffer travels
+        along unused).  Everything is enqueued on the CURRENT stream."""
+        import ctypes as C
+        if self.mode != "allgather":
+            raise RuntimeError("exchange_grids / exchange_tail: allgather mode only")
+        L, lib = self.L, self.L.lib()
+        st = C.c_void_p(L.stream_ptr(self.device))
+        with L.device_guard(self.device):
+            sp = self.send.data_ptr()
+            for i, k in enumerate(self.keys):
+                ob, op, orow = self.off[k]
+                L.check(lib.pn_sparse_rows_pack(C.c_void_p(grid_grads[k].data_ptr()), C.c_int64(self.V[k]), C.c_void_p(sp + 4 * ob),
+                                                C.c_void_p(sp + 4 * op), C.c_void_p(sp + 4 * orow), C.c_int64(self.cap[k]),
+                                                C.c_void_p(self.scratch.data_ptr()), C.c_void_p(self.count[i:].data_ptr()),
+                                                C.c_void_p(self.overflow.data_ptr()), st), "pn_sparse_rows_pack")
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.recv, self.send)
+            else:
+                self.recv.copy_(self.send)
+            for k in self.keys:
+                bm, pf, rows = self._ptrs[k]
+                L.check(lib.pn_sparse_rows_apply(C.c_void_p(grid_grads[k].data_ptr()), C.c_int64(self.V[k]), self.world, bm, pf, rows,
+                                                 C.c_int64(self.cap[k]), st), "pn_sparse_rows_apply")
+
+    def exchange_tail(self, tail_out: torch.Tensor) -> None:
+        """Sum the dense tail (written to ``tail_view()`` beforehand) over the ranks in rank order into ``tail_out``: one small
+        all-gather of the tails + pn_dense_sum."""
+        import ctypes as C
+        if self.mode != "allgather":
+            raise RuntimeError("exchange_grids / exchange_tail: allgather mode only")
+        if not self.tail_numel:
+            return
+        L, lib = self.L, self.L.lib()
+        n = (self.tail_numel + 31) // 32 * 32
+        if getattr(self, "_tail_recv", None) is None:
+            self._tail_recv = torch.zeros(self.world * n, dtype=torch.float32, device=self.device)
+            PtrArr = C.c_void_p * self.world
+            self._tail_recv_ptrs = PtrArr(*[self._tail_recv.data_ptr() + 4 * r * n for r in range(self.world)])
+        mine = self.send[self.off_tail:self.off_tail + n]
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._tail_recv, mine)
+        else:
+            self._tail_recv.copy_(mine)
+        with L.device_guard(self.device):
+            L.check(lib.pn_dense_sum(C.c_void_p(tail_out.data_ptr()), C.c_int64(self.tail_numel), self.world, self._tail_recv_ptrs,
+                                     C.c_void_p(L.stream_ptr(self.device))), "pn_dense_sum")
+
     def check_overflow(self) -> None:
         n = int(self.overflow.item())
         if n:

@@ -388,23 +388,29 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
     # gradient sinks outlive this call: allocated here, on the caller's stream (see plan_forward)
     sinks = [zeros_like_flat(p.params) if (want_w[i] and p.kind != "imap") else None for i, p in enumerate(plan.passes)]
 
-    def run_pass(i, p):
+    g_params.extend([None] * len(plan.passes))
+    # scratch between a pass's input-gradient kernel and its weight-gradient kernel: allocated here, on the caller's stream
+    scratch: List[Optional[dict]] = [None] * len(plan.passes)
+    for i, p in enumerate(plan.passes):
+        if want_w[i] and p.kind != "imap":
+            f32 = dict(dtype=torch.float32, device=device)
+            ws = dict(GH=torch.empty(5 * 32 * n, **f32), GARG=torch.empty(96 * n, **f32),
+                      P32=torch.empty(3 * n, **f32), GO=torch.empty(4 * n, **f32))
+            # GA is neither written nor read for c_dim 32 (pnslam.h, pn_wscratch): alias it
+            tc32 = p.kind == "grid" and p.c_dim == 32
+            ws["GA"] = ws["GH"] if tc32 else torch.empty(5 * 32 * n, **f32)
+            scratch[i] = ws
+
+    def run_input_grad(i, p):
             st = C.c_void_p(L.stream_ptr(device))      # the stream that is current for THIS pass
             nb = host_bound(p.norm_bound)
             gg = g_grids.get(p.grid_a) if p.grid_a else None
             if p.kind == "imap":
                 from . import imap
-                g_params.append(imap.backward(p, pts, g_raw, stashes[i], g_pts, plan.mask_bound, device, bool(want_w[i])))
+                g_params[i] = imap.backward(p, pts, g_raw, stashes[i], g_pts, plan.mask_bound, device, bool(want_w[i]))
                 return
-            ws = wst = None
-            if want_w[i]:
-                f32 = dict(dtype=torch.float32, device=device)
-                ws = dict(GH=torch.empty(5 * 32 * n, **f32), GARG=torch.empty(96 * n, **f32),
-                          P32=torch.empty(3 * n, **f32), GO=torch.empty(4 * n, **f32))
-                # GA is neither written nor read for c_dim 32 (pnslam.h, pn_wscratch): alias it
-                tc32 = p.kind == "grid" and p.c_dim == 32
-                ws["GA"] = ws["GH"] if tc32 else torch.empty(5 * 32 * n, **f32)
-                wst = L.PnWscratch(*[ws[k].data_ptr() for k in ("GA", "GH", "GARG", "P32", "GO")])
+            ws = scratch[i]
+            wst = L.PnWscratch(*[ws[k].data_ptr() for k in ("GA", "GH", "GARG", "P32", "GO")]) if ws is not None else None
             sst = stashes[i].struct()
             if p.kind == "grid":
                 m = _mlp_struct(p)
@@ -415,39 +421,46 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
                                                 C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_grid_mlp_bwd")
                 if GRAD_READY_HOOK is not None and gg is not None:
                     GRAD_READY_HOOK(p.grid_a, gg)          # this grid's gradient is final (one pass writes each grid)
-                if want_w[i]:
-                    gp = sinks[i]
-                    g = L.PnGridMlpGrad()
-                    g.B = gp[0].data_ptr()
-                    for k in range(5):
-                        g.W[k] = gp[1 + k].data_ptr(); g.b[k] = gp[6 + k].data_ptr()
-                        g.Wc[k] = gp[11 + k].data_ptr(); g.bc[k] = gp[16 + k].data_ptr()
-                    g.Wo, g.bo = gp[21].data_ptr(), gp[22].data_ptr()
-                    with L.timed(f"grid_mlp_wgrad:{p.dec.name}", device):
-                        L.check(lib.pn_grid_mlp_wgrad(C.c_int64(n), C.byref(m), C.byref(sst), C.byref(wst), C.byref(g), st),
-                                "pn_grid_mlp_wgrad")
-                    if GRAD_READY_HOOK is not None:
-                        GRAD_READY_HOOK(("params", p.dec.name), gp)
-                    g_params.append(gp)
-                else:
-                    g_params.append(None)
             else:  # coarse
                 m = _coarse_struct(p)
                 ga = _pn_grid(grids_cl[p.grid_a])
                 L.check(lib.pn_coarse_mlp_bwd(C.byref(ps), C.byref(m), C.byref(ga), nb, mb, apply_mask,
                                               C.c_void_p(g_raw.data_ptr()), C.byref(sst), C.c_void_p(L.ptr(gg)),
                                               C.c_void_p(L.ptr(g_pts)), 1, _byref(wst), st), "pn_coarse_mlp_bwd")
-                if want_w[i]:
-                    gp = sinks[i]
-                    g = L.PnCoarseMlpGrad()
-                    for k in range(5):
-                        g.W[k] = gp[k].data_ptr(); g.b[k] = gp[5 + k].data_ptr()
-                    g.Wo, g.bo = gp[10].data_ptr(), gp[11].data_ptr()
-                    L.check(lib.pn_coarse_mlp_wgrad(C.c_int64(n), C.byref(sst), C.byref(wst), C.byref(g), st),
-                            "pn_coarse_mlp_wgrad")
-                    g_params.append(gp)
-                else:
-                    g_params.append(None)
+
+    def run_weight_grad(i, p):
+            if not want_w[i] or p.kind == "imap":
+                return
+            st = C.c_void_p(L.stream_ptr(device))
+            ws = scratch[i]
+            wst = L.PnWscratch(*[ws[k].data_ptr() for k in ("GA", "GH", "GARG", "P32", "GO")])
+            sst = stashes[i].struct()
+            gp = sinks[i]
+            if p.kind == "grid":
+                m = _mlp_struct(p)
+                g = L.PnGridMlpGrad()
+                g.B = gp[0].data_ptr()
+                for k in range(5):
+                    g.W[k] = gp[1 + k].data_ptr(); g.b[k] = gp[6 + k].data_ptr()
+                    g.Wc[k] = gp[11 + k].data_ptr(); g.bc[k] = gp[16 + k].data_ptr()
+                g.Wo, g.bo = gp[21].data_ptr(), gp[22].data_ptr()
+                with L.timed(f"grid_mlp_wgrad:{p.dec.name}", device):
+                    L.check(lib.pn_grid_mlp_wgrad(C.c_int64(n), C.byref(m), C.byref(sst), C.byref(wst), C.byref(g), st),
+                            "pn_grid_mlp_wgrad")
+                if GRAD_READY_HOOK is not None:
+                    GRAD_READY_HOOK(("params", p.dec.name), gp)
+            else:  # coarse
+                g = L.PnCoarseMlpGrad()
+                for k in range(5):
+                    g.W[k] = gp[k].data_ptr(); g.b[k] = gp[5 + k].data_ptr()
+                g.Wo, g.bo = gp[10].data_ptr(), gp[11].data_ptr()
+                L.check(lib.pn_coarse_mlp_wgrad(C.c_int64(n), C.byref(sst), C.byref(wst), C.byref(g), st),
+                        "pn_coarse_mlp_wgrad")
+            g_params[i] = gp
+
+    def run_pass(i, p):
+            run_input_grad(i, p)
+            run_weight_grad(i, p)
 
     # The passes of a stage are independent given g_raw (each writes its own grid and parameter gradients; the point
     # gradient is accumulated with atomics), so the first pass (+ its weight gradients) runs on the current stream and
@@ -462,6 +475,26 @@ def plan_backward(plan: Plan, grids_cl: Dict[str, torch.Tensor], pts: Points, de
             side.wait_stream(main)
         cost = [_BWD_COST.get(p.dec.name if p.kind == "grid" else p.kind, 1.0) + (_WGRAD_COST if want_w[i] else 0.0)
                 for i, p in enumerate(plan.passes)]
+        if GRIDS_READY_HOOK is not None and side is not None and SM_SPLIT and any(want_w):
+            # Data-parallel mapper: every INPUT-gradient kernel first (pass 0 beside the chain of the others, SM shares by
+            # cost), then the hook -- all grid gradients are final, it starts their exchange on another stream -- and only
+            # then the weight-gradient kernels, which run while the exchange is in flight (on the SMs the hook leaves them).
+            share = _sm_shares(sum(_BWD_COST.get(p.dec.name if p.kind == "grid" else p.kind, 1.0) for p in plan.passes[1:]),
+                               _BWD_COST.get(plan.passes[0].dec.name if plan.passes[0].kind == "grid" else plan.passes[0].kind, 1.0))
+            for i, p in enumerate(plan.passes):
+                if i >= 1:
+                    with torch.cuda.stream(side), _sm_budget(share[0]):
+                        run_input_grad(i, p)
+                else:
+                    with _sm_budget(share[1]):
+                        run_input_grad(i, p)
+            main.wait_stream(side)
+            leave = int(GRIDS_READY_HOOK(g_grids) or 0)
+            full = sum(_sm_shares(1.0, 1.0))
+            with _sm_budget(max(1, full - leave) if leave > 0 else None):
+                for i, p in enumerate(plan.passes):
+                    run_weight_grad(i, p)
+            return g_grids, g_pts, g_params
         n_chains = BWD_STREAMS if BWD_STREAMS > 0 else (2 if any(want_w) else 3)
         three = side is not None and SM_SPLIT and n_chains >= 3 and len(plan.passes) == 3
         if three:      # one chain per pass, SMs in proportion to the passes' costs
@@ -561,6 +594,10 @@ def _side_stream(device, which: int = 0) -> "torch.cuda.Stream":
 # flat buffer).  dist.OverlappedGradReducer uses it to start the NCCL all-reduce of a finished
 # gradient while the remaining decoder kernels still run.
 GRAD_READY_HOOK = None
+# Optional callback ``hook(g_grids) -> SMs to leave free`` fired from inside the backward once EVERY grid gradient is final and
+# before the weight-gradient kernels are launched (they are deferred to after the hook): mapping.MappingIteration starts the
+# sparse row exchange of the grid gradients there, so that it overlaps the weight-gradient kernels.
+GRIDS_READY_HOOK = None
 
 
 class FlatGrads(list):

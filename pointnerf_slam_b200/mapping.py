@@ -15,6 +15,7 @@ synchronises with the host.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -66,6 +67,10 @@ class MappingIteration:
         self.last_indices = None
         self._batch: Optional[KeyframeBatch] = None
         self._arena_join = None
+        self._comm_pending = None
+        # sparse (all-gather) exchange: start it as soon as the grid gradients are final, beside the weight-gradient kernels
+        self.overlap_exchange = os.environ.get("PN_OVERLAP_EXCHANGE", "0") != "0"
+        self.overlap_reserve_sms = int(os.environ.get("PN_OVERLAP_RESERVE_SMS", "16"))
 
     # ------------------------------------------------------------------------------------------
     def trained(self) -> List[torch.Tensor]:
@@ -130,20 +135,14 @@ class MappingIteration:
             off += n
         return torch.as_strided(tensors[0], (off,), (1,))
 
-    def _exchange_sparse(self):
-        """Sum the gradients over the ranks through dist.SparseGradExchange.  With the gradient arena the three grid
-        gradients are one contiguous [V_total][32] block and the decoder gradients one flat slice, so the whole exchange
-        is: pack (3 launches), tail copies, ONE all-gather (or none: P2P), apply, tail sums."""
-        grid_grads = []
-        for k in self.grid_keys:
-            g = self.grids[k].grad
+    def _sparse_setup(self, grid_grads):
+        """(exchange object, key -> gradient block): with the gradient arena the grid gradients are ONE contiguous
+        [V_total][32] block ("grids"), otherwise one block per grid."""
+        for k, g in zip(self.grid_keys, grid_grads):
             if not g.is_contiguous(memory_format=torch.channels_last_3d):
                 raise RuntimeError(f"{k}: sparse exchange needs the channels-last gradient the backward produces")
-            grid_grads.append(g)
         order = sorted(range(len(grid_grads)), key=lambda i: grid_grads[i].data_ptr())
         flat_grids = self._contiguous_block([grid_grads[i] for i in order], [grid_grads[i].numel() for i in order])
-        pgrads = [p.grad for p in self.dec_params]
-        flat_params = self._contiguous_block(pgrads, [(p.numel() + 3) // 4 * 4 for p in self.dec_params]) if pgrads else None
         if self._sparse is None:
             if flat_grids is not None:
                 shapes = {"grids": (flat_grids.numel() // 32, 1, 1)}
@@ -153,9 +152,15 @@ class MappingIteration:
             self._sparse = D.SparseGradExchange(shapes, tail, self.device, cap_frac=self.sparse_cap_frac,
                                                 mode="p2p" if self.exchange == "sparse_p2p" else "allgather", world=self.world)
             self._sparse_flat = flat_grids is not None
-        sp = self._sparse
         if self._sparse_flat != (flat_grids is not None):
             raise RuntimeError("sparse exchange: the gradient buffers changed layout between iterations")
+        return self._sparse, ({"grids": flat_grids} if flat_grids is not None else dict(zip(self.grid_keys, grid_grads)))
+
+    def _fill_tail(self, sp):
+        """Copy the decoder / shared-camera gradients into the exchange's dense tail; returns (flat_params or None,
+        pgrads, cam_grads)."""
+        pgrads = [p.grad for p in self.dec_params]
+        flat_params = self._contiguous_block(pgrads, [(p.numel() + 3) // 4 * 4 for p in self.dec_params]) if pgrads else None
         tail = sp.tail_view()
         cam_grads = [c.grad for c in self.shared_cams]
         n_par = sum((p.numel() + 3) // 4 * 4 for p in self.dec_params)
@@ -166,13 +171,49 @@ class MappingIteration:
         cam_views = [tail[o:o + c.numel()] for o, c in zip(self._tail_off[len(self.dec_params):], self.shared_cams)]
         if cam_grads:
             torch._foreach_copy_(cam_views, cam_grads)
-        summed = torch.empty_like(tail) if (flat_params is None or cam_grads) else None
-        if flat_params is not None and not cam_grads:
-            sp.exchange({"grids": flat_grids} if flat_grids is not None else dict(zip(self.grid_keys, grid_grads)), flat_params)
-            return
-        sp.exchange({"grids": flat_grids} if flat_grids is not None else dict(zip(self.grid_keys, grid_grads)), summed)
+        return flat_params, pgrads, cam_grads
+
+    def _scatter_tail(self, summed, pgrads, cam_grads):
         outs = [summed[o:o + p.numel()].view(p.shape) for o, p in zip(self._tail_off, self._tail_items)]
         torch._foreach_copy_(pgrads + cam_grads, outs)
+
+    def _exchange_sparse(self):
+        """Sum the gradients over the ranks through dist.SparseGradExchange.  With the gradient arena the three grid
+        gradients are one contiguous [V_total][32] block and the decoder gradients one flat slice, so the whole exchange
+        is: pack (3 launches), tail copies, ONE all-gather (or none: P2P), apply, tail sums."""
+        sp, blocks = self._sparse_setup([self.grids[k].grad for k in self.grid_keys])
+        flat_params, pgrads, cam_grads = self._fill_tail(sp)
+        if flat_params is not None and not cam_grads:
+            sp.exchange(blocks, flat_params)
+            return
+        summed = torch.empty_like(sp.tail_view())
+        sp.exchange(blocks, summed)
+        self._scatter_tail(summed, pgrads, cam_grads)
+
+    # -- overlapped variant: the grid rows travel while the weight-gradient kernels run -------------------------------
+    def _on_grids_ready(self, g_grids) -> int:
+        """engine.GRIDS_READY_HOOK: every grid gradient is final, the weight-gradient kernels have not been launched yet.
+        Start the row exchange on the communication stream; returns the SMs the remaining kernels should leave free."""
+        sp, blocks = self._sparse_setup([g_grids[k] for k in self.grid_keys])
+        main, comm = torch.cuda.current_stream(self.device), E._side_stream(self.device, 3)
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            sp.exchange_grids(blocks)
+        self._comm_pending = comm
+        return self.overlap_reserve_sms
+
+    def _finish_overlapped(self):
+        """After the backward: exchange the dense tail (decoder + shared-camera gradients), then join the row exchange."""
+        sp = self._sparse
+        flat_params, pgrads, cam_grads = self._fill_tail(sp)
+        if flat_params is not None and not cam_grads:
+            sp.exchange_tail(flat_params)
+        else:
+            summed = torch.empty_like(sp.tail_view())
+            sp.exchange_tail(summed)
+            self._scatter_tail(summed, pgrads, cam_grads)
+        torch.cuda.current_stream(self.device).wait_stream(self._comm_pending)
+        self._comm_pending = None
 
     def __call__(self, indices=None) -> torch.Tensor:
         if self.arena is not None:
@@ -193,6 +234,16 @@ class MappingIteration:
                     loss = self._backward(indices)
                 self._reducer.finish({k: self.grids[k] for k in self.grid_keys}, decoders=dict(self.dec_modules),
                                      others=[c.grad for c in self.shared_cams])
+            elif self._use_sparse and self.exchange == "sparse" and self.overlap_exchange and E.SM_SPLIT and E.PARALLEL_BACKWARD:
+                E.GRIDS_READY_HOOK = self._on_grids_ready
+                try:
+                    loss = self._backward(indices)
+                finally:
+                    E.GRIDS_READY_HOOK = None
+                if self._comm_pending is not None:
+                    self._finish_overlapped()
+                else:                       # the backward did not take the deferred path (no weight gradients asked for)
+                    self._exchange_sparse()
             else:
                 loss = self._backward(indices)
                 if self._use_sparse:

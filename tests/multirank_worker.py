@@ -20,10 +20,13 @@ def main(out_path, exchange, sharding):
     rank, world, local = D.init_from_env()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    E.PARALLEL_BACKWARD = False
+    overlap = exchange == "sparse_overlap"    # the row exchange starts inside the backward, beside the weight-gradient kernels
+    E.PARALLEL_BACKWARD = overlap
     pix = 400
     shared = sharding == "rays"
-    w = B.build_mapping(dev, 0 if shared else rank, world, pix, exchange, with_optimizer=False, shared_cameras=shared)
+    w = B.build_mapping(dev, 0 if shared else rank, world, pix, "sparse" if overlap else exchange, with_optimizer=False,
+                        shared_cameras=shared)
+    w.iteration.overlap_exchange = overlap
     g = torch.Generator().manual_seed(100 + rank)
     idx = [torch.randint(B.H * B.W, (pix,), generator=g).to(dev) for _ in range(B.N_KEYFRAMES)]
     for rep in range(2):                      # twice: buffers of the exchange are reused across iterations
@@ -49,6 +52,7 @@ def main(out_path, exchange, sharding):
     res = None
     if rank == 0:
         E.GRAD_ARENA = None
+        E.PARALLEL_BACKWARD = False
         ws = [B.build_mapping(dev, 0 if shared else r, 1, pix, "none", with_optimizer=False, arena=False) for r in range(world)]
         w0 = ws[0]
         if shared:    # one batch: frame k gets the pixels of every rank

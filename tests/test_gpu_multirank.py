@@ -25,7 +25,7 @@ def _run(tmp_path, exchange, sharding, world=2):
     return json.load(open(out))
 
 
-@pytest.mark.parametrize("exchange", ["sparse", "sparse_p2p", "overlap", "arena", "dense"])
+@pytest.mark.parametrize("exchange", ["sparse", "sparse_overlap", "sparse_p2p", "overlap", "arena", "dense"])
 @pytest.mark.parametrize("sharding", ["rays", "keyframes"])
 def test_sharded_gradients_equal_single_gpu(tmp_path, exchange, sharding):
     res = _run(tmp_path, exchange, sharding)
