@@ -10,6 +10,17 @@ import bench as B
 from tests import helpers as T
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _box_independent_oracle():
+    """The oracle runs on this box's CPU: pin the evaluation order of its Fourier argument (oracle/nice_oracle.py, EMBED_ORDER)
+    so that the comparison does not depend on the host's BLAS."""
+    from oracle import nice_oracle as NO
+    with NO.fixed_embed_order():
+        yield
+
+
 DEV = torch.device("cuda", 0)
 
 
