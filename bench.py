@@ -88,7 +88,9 @@ ROOFLINE_NOTE = ("decoder layers run on tcgen05 (kind::tf32, 3xTF32 split, FP32 
                  "weight-gradient kernel) and by the latency of the 5-9 dependent MMA round trips per tile, not by HBM; the grids "
                  "(46 MiB) are L2-resident, so DRAM traffic is far below the algorithmic bytes; HBM roofline is the BASELINE.md denominator")
 ROOFLINE_NOTE_KNN = ("integer/float32 search + gather: no GEMM, SIMT kernels only; the candidate scan of the 27 neighbouring cells "
-                     "(~150 position records per sample, L1/L2 hits) is not part of the algorithmic bytes")
+                     "(~150 position records per sample, L1/L2 hits) is not part of the algorithmic bytes; kernel_frac_of_hbm of knn_bwd "
+                     "exceeds 1 because its algorithmic bytes (8 row read-modify-writes + 8 row re-reads per sample) mostly hit L2: "
+                     "neighbouring samples share neighbours (measured DRAM traffic 70 MB per launch, profiles/r2_ncu_knn_summary.txt)")
 
 
 def workload_name(scaling="weak"):

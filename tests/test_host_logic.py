@@ -170,3 +170,40 @@ def test_mapper_side_entry_points_fail_loudly_on_cpu():
         PM.prefilter_mask(torch.zeros(4, 3), torch.ones(4, 3), torch.ones(4), torch.tensor([[0.0, 1.0]] * 3))
     with pytest.raises(RuntimeError, match="CUDA"):
         PM.select_depth_pixels(torch.zeros(8, 8), 0, 8, 0, 8)
+
+
+def test_round2_entry_points_fail_loudly_on_cpu():
+    """k-NN aggregation, the gradient-returning loss heads and the iteration callables: CUDA tensors or an exception."""
+    import pointnerf_slam_b200.knn as PK
+    from pointnerf_slam_b200.tracking import TrackingIteration
+    xyz, feat = torch.rand(10, 3), torch.zeros(10, 32)
+    bound = [[0.0, 1.0]] * 3
+    with pytest.raises(RuntimeError, match="CUDA tensor required"):
+        PK.NeuralPointIndex(xyz, bound, 0.2)
+    with pytest.raises(RuntimeError, match="CUDA tensor required"):
+        PK.NeuralPointField(xyz, feat, bound, 0.2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        P.losses.mapping_loss_and_grads(torch.zeros(4, dtype=torch.float64), torch.zeros(4, 3), torch.ones(4), torch.zeros(4, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        P.losses.tracking_loss_and_grads(torch.zeros(4, dtype=torch.float64), torch.ones(4, dtype=torch.float64), torch.zeros(4, 3),
+                                         torch.ones(4), torch.zeros(4, 3))
+    if not torch.cuda.is_available():
+        cam = torch.tensor([1.0, 0, 0, 0, 0, 0, 0], requires_grad=True)
+        it = TrackingIteration(None, None, {}, torch.ones(8, 8), torch.zeros(8, 8, 3), cam, 8, 8, 8.0, 8.0, 3.5, 3.5, 4)
+        with pytest.raises(Exception):
+            it()
+
+
+def test_knn_struct_matches_the_header():
+    """ctypes mirror of pn_knn_index: field order and sizes as declared in include/pnslam.h."""
+    import ctypes as C
+    import pointnerf_slam_b200.knn as PK
+    names = [f[0] for f in PK.PnKnnIndex._fields_]
+    assert names == ["start", "sorted", "lo", "inv_h", "nx", "ny", "nz", "P"]
+    assert C.sizeof(PK.PnKnnIndex) == 8 + 8 + 12 + 4 + 16
+    hdr = open(L.HEADER_PATH).read()
+    body = hdr[hdr.index("typedef struct pn_knn_index {"):hdr.index("} pn_knn_index;")]
+    order = [body.index(k) for k in ("start;", "sorted;", "lo[3];", "inv_h;", "nx, ny, nz;", "int P;")]
+    assert order == sorted(order)
+    for fn in ("pn_knn_build", "pn_knn_query", "pn_knn_aggregate_fwd", "pn_knn_aggregate_bwd"):
+        assert hasattr(L.lib(), fn) and getattr(L.lib(), fn).argtypes is not None
