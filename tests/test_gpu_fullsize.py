@@ -71,12 +71,13 @@ def test_full_size_forward_matches_oracle(world):
     with torch.no_grad():
         d, v, c = w.renderer.render_batch_ray(w.grids, w.model, rd, ro, DEV, "color", gt_depth=gd)
         dr, vr, cr = O.render_batch_ray(_oracle_scene(w), rd.cpu(), ro.cpu(), "color", gd.cpu())
-    # tight tolerance for 99.9 % of the rays (~10x the typical error), loose bound for the rest: the oracle's own float32
-    # sin(p.B) at arguments of hundreds of radians moves by 1e-4 with the summation order of its sgemm, and this scene
-    # (grids x20, lively biases) amplifies that into the 1e-3 range for a handful of rays
-    print(T.assert_close_q(d, dr, rtol=3e-5, atol=3e-6, rtol_max=1e-3, atol_max=3e-4, what="depth"))
-    print(T.assert_close_q(c, cr, rtol=1e-4, atol=3e-5, rtol_max=1e-2, atol_max=3e-3, q=0.995, what="colour"))
-    print(T.assert_close_q(v, vr, rtol=3e-4, atol=3e-6, rtol_max=3e-3, atol_max=3e-4, q=0.995, what="variance"))
+    # The oracle evaluates its Fourier argument in the kernels' order (module fixture), so the comparison no longer carries the
+    # 1e-4 noise of the host BLAS's summation order: measured on a B200 box max 2.9e-6 (depth), 4.8e-6 (colour), 8.6e-6
+    # (variance) of the largest value, all rays inside the tight bound.  Tight bound for 99.9 % of the rays, a bound ~20x the
+    # measured maximum for every ray.
+    print(T.assert_close_q(d, dr, rtol=3e-5, atol=3e-6, rtol_max=3e-4, atol_max=1e-4, what="depth"))
+    print(T.assert_close_q(c, cr, rtol=1e-4, atol=3e-5, rtol_max=1e-3, atol_max=3e-4, q=0.999, what="colour"))
+    print(T.assert_close_q(v, vr, rtol=3e-4, atol=3e-6, rtol_max=3e-3, atol_max=3e-4, q=0.999, what="variance"))
     assert (gd == 0).sum() > 20, "the zero-depth sampling branch must be exercised"
 
 
