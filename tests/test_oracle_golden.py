@@ -77,3 +77,30 @@ def test_imap_with_shipped_weights():
     for k, v in sd.items():
         gk = g["gradsd/" + k]
         assert T.rel_max(v.grad, gk) < 1e-3, k
+
+
+def test_fixed_embed_order_is_an_admissible_order_of_the_reference_matmul():
+    """EMBED_ORDER='fma' (used by the full-size GPU comparisons) evaluates p @ B as one fused x-y-z chain: per element it may
+    differ from the box's BLAS by the last bit of the argument only, and its gradients are those of the matmul."""
+    g = torch.Generator().manual_seed(0)
+    p = (torch.rand(4000, 3, generator=g) * 10 - 4).requires_grad_(True)
+    B = (torch.randn(3, O.EMBED, generator=g) * 25).requires_grad_(True)
+    ref = O.fourier_embed(p, B)
+    gw = torch.randn(ref.shape, generator=g)
+    (ref * gw).sum().backward()
+    gp, gB = p.grad.clone(), B.grad.clone()
+    p.grad = B.grad = None
+    assert O.EMBED_ORDER is None
+    with O.fixed_embed_order():
+        assert O.EMBED_ORDER == "fma"
+        out = O.fourier_embed(p, B)
+    assert O.EMBED_ORDER is None
+    arg = (p.detach().double() @ B.detach().double())
+    # rounding of the partial sums: relative to the magnitude of the terms, not of the (possibly cancelled) result
+    ulp = torch.finfo(torch.float32).eps * (p.detach().double().abs() @ B.detach().double().abs()).clamp_min(1.0)
+    # |sin a - sin b| <= |a - b|: both float32 evaluations lie within 2 ulps (of the terms) of the exact argument
+    assert bool(((out.detach().double() - torch.sin(arg)).abs() <= 2 * ulp + 1e-6).all())
+    assert bool(((ref.detach().double() - torch.sin(arg)).abs() <= 2 * ulp + 1e-6).all())
+    (out * gw).sum().backward()
+    assert torch.allclose(p.grad, gp, rtol=1e-3, atol=1e-2 * gp.abs().max().item())
+    assert torch.allclose(B.grad, gB, rtol=1e-3, atol=1e-2 * gB.abs().max().item())
